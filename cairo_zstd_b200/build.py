@@ -1,0 +1,54 @@
+"""Builds libcairo_zstd_b200.so in-tree with nvcc for sm_100a (no torch dependency)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libcairo_zstd_b200.so")
+SOURCES = ["czb_api.cu", "czb_handle.cu", "k_scan.cu", "k_huff.cu", "k_fse.cu", "k_exec.cu", "k_xxh.cu"]
+HEADERS = ["czb_internal.cuh", "czb_parse.cuh", "czb_fse_build.cuh", "czb_host.h",
+           "../../include/cairo_zstd_b200.h", "../../include/czstd_status.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math"]
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not (force or stale()):
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    for s in SOURCES:
+        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    fail = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append(f"==== {s}\n{out}")
+        if p.returncode != 0:
+            fail = True
+    text = "\n".join(log)
+    open(os.path.join(HERE, "build", "ptxas.log"), "w").write(text)
+    if fail or verbose:
+        print(text, file=sys.stderr if fail else sys.stdout)
+    if fail:
+        raise RuntimeError("nvcc failed")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(LIB)

@@ -1,0 +1,391 @@
+// czb_api.cu -- host side of the C ABI: context, workspace planning, batch entry points.
+// (The FrameDecoder handle mirror lives in czb_handle.cu.)
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "czb_host.h"
+#include "czb_internal.cuh"
+#include "czb_parse.cuh"
+
+namespace czb {
+int setup_huff_attributes();
+int setup_fse_attributes();
+}  // namespace czb
+
+using namespace czb;
+
+#define CZB_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e__);          \
+            return CZS_CUDA_ERROR;                                                            \
+        }                                                                                     \
+    } while (0)
+
+template <typename T>
+static int ensure(czb_context* ctx, DevBuf<T>& b, uint64_t n) {
+    if (n <= b.cap) return CZS_OK;
+    uint64_t want = std::max<uint64_t>(n, b.cap + b.cap / 2);
+    if (b.p) CZB_CUDA(ctx, cudaFree(b.p));  // cudaFree synchronises the device: no kernel still uses it
+    b.p = nullptr; b.cap = 0;
+    CZB_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b.p), want * sizeof(T)));
+    b.cap = want;
+    return CZS_OK;
+}
+
+extern "C" int czb_abi_version(void) { return CZB_ABI_VERSION; }
+
+extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out) {
+    if (!out) return CZS_BAD_ARGUMENT;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) return CZS_CUDA_ERROR;
+    czb_context* ctx = new czb_context();
+    ctx->device = device;
+    ctx->budget = budget ? budget : (8ull << 30);
+    ctx->wave_frames = 65536;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0) { delete ctx; return CZS_CUDA_ERROR; }
+    if (cudaMallocHost(reinterpret_cast<void**>(&ctx->totals_h), sizeof(WaveTotals) * kMaxWaves) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    *out = ctx;
+    return CZS_OK;
+}
+
+extern "C" void czb_context_destroy(czb_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p); cudaFree(ctx->blocks.p); cudaFree(ctx->huf_items.p);
+    cudaFree(ctx->fse_items.p); cudaFree(ctx->lit.p); cudaFree(ctx->seq.p); cudaFree(ctx->counters.p);
+    cudaFree(ctx->h_descs.p); cudaFree(ctx->h_results.p);
+    for (int s = 0; s < 2; s++) { cudaFree(ctx->h_src[s].p); cudaFree(ctx->h_dst[s].p); }
+    if (ctx->totals_h) cudaFreeHost(ctx->totals_h);
+    if (ctx->pin_a) cudaFreeHost(ctx->pin_a);
+    if (ctx->pin_b) cudaFreeHost(ctx->pin_b);
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    delete ctx;
+}
+
+extern "C" const char* czb_last_error(const czb_context* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+extern "C" uint64_t czb_kernel_launches(const czb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+static uint64_t wave_scratch_bytes(const WaveTotals& t) {
+    return t.n_blocks * sizeof(BlockDesc) + t.lit_bytes + t.n_seq * sizeof(Seq) + (t.n_huf + t.n_fse) * 4;
+}
+
+// The hot path.  descs/results are device arrays.
+extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
+                                       uint32_t flags, void* stream_v) {
+    if (!ctx || (n && (!descs || !results))) return CZS_BAD_ARGUMENT;
+    if (n == 0) return CZS_OK;
+    if (n > 0xFFFFFF00ull) { ctx->last_error = "more than 2^32 frames per call"; return CZS_BAD_ARGUMENT; }
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    LaunchCtx lc{stream, &ctx->launches};
+    int rc;
+    if ((rc = ensure(ctx, ctx->infos, n))) return rc;
+    if ((rc = ensure(ctx, ctx->totals_d, kMaxWaves))) return rc;
+    if ((rc = ensure(ctx, ctx->counters, 1))) return rc;
+
+    // ---- plan: scan every frame, then size waves so that scratch fits the budget ----
+    uint64_t W = std::min<uint64_t>((n + 127) / 128 * 128, ctx->wave_frames);
+    while ((n + W - 1) / W > kMaxWaves) W *= 2;
+    uint64_t n_waves = 0;
+    for (int attempt = 0;; attempt++) {
+        n_waves = (n + W - 1) / W;
+        if (attempt == 0) {
+            CZB_CUDA(ctx, cudaMemsetAsync(ctx->totals_d.p, 0, n_waves * sizeof(WaveTotals), stream));
+            launch_scan_frames(lc, descs, ctx->infos.p, n, W, ctx->totals_d.p);
+        } else {
+            launch_wave_totals(lc, ctx->infos.p, n, W, ctx->totals_d.p, n_waves);
+        }
+        CZB_CUDA(ctx, cudaMemcpyAsync(ctx->totals_h, ctx->totals_d.p, n_waves * sizeof(WaveTotals), cudaMemcpyDeviceToHost, stream));
+        CZB_CUDA(ctx, cudaStreamSynchronize(stream));
+        uint64_t worst = 0;
+        for (uint64_t w = 0; w < n_waves; w++) worst = std::max(worst, wave_scratch_bytes(ctx->totals_h[w]));
+        if (worst <= ctx->budget || W <= 128 || (n + W / 2 - 1) / (W / 2) > kMaxWaves) break;
+        W = std::max<uint64_t>(128, (W / 2 + 127) / 128 * 128);
+    }
+    WaveTotals mx{};
+    for (uint64_t w = 0; w < n_waves; w++) {
+        const WaveTotals& t = ctx->totals_h[w];
+        mx.n_blocks = std::max(mx.n_blocks, t.n_blocks); mx.lit_bytes = std::max(mx.lit_bytes, t.lit_bytes);
+        mx.n_seq = std::max(mx.n_seq, t.n_seq); mx.n_huf = std::max(mx.n_huf, t.n_huf); mx.n_fse = std::max(mx.n_fse, t.n_fse);
+        if (t.n_blocks > 0xFFFFFF00ull) { ctx->last_error = "too many blocks in one wave"; return CZS_UNSUPPORTED; }
+    }
+    if ((rc = ensure(ctx, ctx->blocks, mx.n_blocks + 1))) return rc;
+    if ((rc = ensure(ctx, ctx->huf_items, mx.n_huf + 1))) return rc;
+    if ((rc = ensure(ctx, ctx->fse_items, mx.n_fse + 1))) return rc;
+    if ((rc = ensure(ctx, ctx->lit, mx.lit_bytes + 64))) return rc;
+    if ((rc = ensure(ctx, ctx->seq, mx.n_seq + 1))) return rc;
+
+    launch_header_results(lc, ctx->infos.p, results, n);
+    for (uint64_t w = 0; w < n_waves; w++) {
+        const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
+        const WaveTotals& t = ctx->totals_h[w];
+        CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(WaveCounters), stream));
+        launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->huf_items.p, ctx->fse_items.p, ctx->counters.p);
+        launch_huff(lc, descs + first, ctx->blocks.p, ctx->huf_items.p, ctx->counters.p, (uint32_t)t.n_huf, ctx->lit.p);
+        launch_fse(lc, descs + first, ctx->blocks.p, ctx->fse_items.p, ctx->counters.p, (uint32_t)t.n_fse, ctx->seq.p);
+        launch_exec(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->lit.p, ctx->seq.p, results);
+        if (flags & CZB_FLAG_VERIFY_CHECKSUM) launch_xxh64(lc, descs, results, first, count);
+        ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count;
+    }
+    CZB_CUDA(ctx, cudaGetLastError());
+    return CZS_OK;
+}
+
+// ---- host-pointer forms ---------------------------------------------------------------------
+static int ensure_pinned(czb_context* ctx, uint8_t*& p, uint64_t& cap, uint64_t n) {
+    if (n <= cap) return CZS_OK;
+    if (p) CZB_CUDA(ctx, cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    CZB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&p), n));
+    cap = n;
+    return CZS_OK;
+}
+
+extern "C" int czb_decode_batch_host(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
+                                     uint32_t flags) {
+    if (!ctx || (n && (!descs || !results))) return CZS_BAD_ARGUMENT;
+    if (n == 0) return CZS_OK;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // gather sources into one pinned staging buffer (16-byte aligned per frame), one H2D copy
+    std::vector<uint64_t> soff(n + 1), doff(n + 1);
+    uint64_t stot = 0, dtot = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        soff[i] = stot; doff[i] = dtot;
+        stot += (descs[i].src_len + 15) & ~15ull;
+        dtot += (descs[i].dst_cap + 15) & ~15ull;
+    }
+    soff[n] = stot; doff[n] = dtot;
+    int rc;
+    if ((rc = ensure_pinned(ctx, ctx->pin_a, ctx->pin_a_cap, stot + 16))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->pin_b, ctx->pin_b_cap, std::max<uint64_t>(n * sizeof(czb_frame_desc), n * sizeof(czb_frame_result))))) return rc;
+    if ((rc = ensure(ctx, ctx->h_src[0], stot + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->h_dst[0], dtot + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->h_descs, n))) return rc;
+    if ((rc = ensure(ctx, ctx->h_results, n))) return rc;
+    for (uint64_t i = 0; i < n; i++)
+        if (descs[i].src_len) memcpy(ctx->pin_a + soff[i], descs[i].src, descs[i].src_len);
+    czb_frame_desc* hd = reinterpret_cast<czb_frame_desc*>(ctx->pin_b);
+    for (uint64_t i = 0; i < n; i++) {
+        hd[i].src = ctx->h_src[0].p + soff[i]; hd[i].src_len = descs[i].src_len;
+        hd[i].dst = ctx->h_dst[0].p + doff[i]; hd[i].dst_cap = descs[i].dst_cap;
+    }
+    cudaStream_t st = ctx->compute;
+    CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_src[0].p, ctx->pin_a, stot, cudaMemcpyHostToDevice, st));
+    CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_descs.p, hd, n * sizeof(czb_frame_desc), cudaMemcpyHostToDevice, st));
+    if ((rc = czb_decode_batch_device(ctx, ctx->h_descs.p, ctx->h_results.p, n, flags, st))) return rc;
+    CZB_CUDA(ctx, cudaMemcpyAsync(ctx->pin_b, ctx->h_results.p, n * sizeof(czb_frame_result), cudaMemcpyDeviceToHost, st));
+    CZB_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(results, ctx->pin_b, n * sizeof(czb_frame_result));
+    // copy back only what was produced, frame by frame for small batches, else one span
+    uint64_t produced_end = 0;
+    for (uint64_t i = 0; i < n; i++) if (results[i].status == CZS_OK && results[i].bytes_written) produced_end = doff[i] + results[i].bytes_written;
+    if (produced_end) {
+        if ((rc = ensure_pinned(ctx, ctx->pin_a, ctx->pin_a_cap, produced_end))) return rc;
+        CZB_CUDA(ctx, cudaMemcpyAsync(ctx->pin_a, ctx->h_dst[0].p, produced_end, cudaMemcpyDeviceToHost, st));
+        CZB_CUDA(ctx, cudaStreamSynchronize(st));
+        for (uint64_t i = 0; i < n; i++)
+            if (results[i].status == CZS_OK && results[i].bytes_written) memcpy(descs[i].dst, ctx->pin_a + doff[i], results[i].bytes_written);
+    }
+    return CZS_OK;
+}
+
+// Packed form: chunked, transfers overlapped with decoding (three streams, two staging slots).
+extern "C" int czb_decode_batch_host_packed(czb_context* ctx, const uint8_t* src_base, const uint64_t* src_off, uint8_t* dst_base,
+                                            const uint64_t* dst_off, czb_frame_result* results, uint64_t n, uint32_t flags) {
+    if (!ctx || (n && (!src_base || !src_off || !dst_base || !dst_off || !results))) return CZS_BAD_ARGUMENT;
+    if (n == 0) return CZS_OK;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // chunk boundaries: bounded staging (src + dst bytes per chunk) and bounded frame count
+    const uint64_t kChunkBytes = ctx->host_chunk_bytes;
+    std::vector<uint64_t> cuts{0};
+    {
+        uint64_t i = 0;
+        while (i < n) {
+            uint64_t j = i + 1;
+            while (j < n && j - i < 65536 && (src_off[j + 1] - src_off[i]) + (dst_off[j + 1] - dst_off[i]) <= kChunkBytes) j++;
+            cuts.push_back(j);
+            i = j;
+        }
+    }
+    const uint64_t n_chunks = cuts.size() - 1;
+    uint64_t max_src = 0, max_dst = 0, max_frames = 0;
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        max_src = std::max(max_src, src_off[cuts[c + 1]] - src_off[cuts[c]]);
+        max_dst = std::max(max_dst, dst_off[cuts[c + 1]] - dst_off[cuts[c]]);
+        max_frames = std::max(max_frames, cuts[c + 1] - cuts[c]);
+    }
+    int rc;
+    for (int s = 0; s < 2; s++) {
+        if ((rc = ensure(ctx, ctx->h_src[s], max_src + 64))) return rc;
+        if ((rc = ensure(ctx, ctx->h_dst[s], max_dst + 64))) return rc;
+    }
+    if ((rc = ensure(ctx, ctx->h_descs, 2 * max_frames))) return rc;
+    if ((rc = ensure(ctx, ctx->h_results, 2 * max_frames))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->pin_b, ctx->pin_b_cap, 2 * max_frames * sizeof(czb_frame_desc)))) return rc;
+    cudaEvent_t ev_in[2], ev_dec[2], ev_out[2];
+    for (int s = 0; s < 2; s++) {
+        CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
+        CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_dec[s], cudaEventDisableTiming));
+        CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming));
+    }
+    auto enqueue_in = [&](uint64_t c) -> int {
+        const int s = (int)(c & 1);
+        const uint64_t f0 = cuts[c], f1 = cuts[c + 1], nf = f1 - f0;
+        // slot s is free once chunk c-2's outputs have been copied out
+        if (c >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_out[s], 0));
+        // the aligned base keeps each frame's alignment relative to src_base
+        const uint64_t sb = src_off[f0], mis = sb & 15;
+        CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_src[s].p + mis, src_base + sb, src_off[f1] - sb, cudaMemcpyHostToDevice, ctx->copy_in));
+        czb_frame_desc* hd = reinterpret_cast<czb_frame_desc*>(ctx->pin_b) + (uint64_t)s * max_frames;
+        const uint64_t db = dst_off[f0], dmis = db & 15;
+        for (uint64_t i = 0; i < nf; i++) {
+            hd[i].src = ctx->h_src[s].p + mis + (src_off[f0 + i] - sb); hd[i].src_len = src_off[f0 + i + 1] - src_off[f0 + i];
+            hd[i].dst = ctx->h_dst[s].p + dmis + (dst_off[f0 + i] - db); hd[i].dst_cap = dst_off[f0 + i + 1] - dst_off[f0 + i];
+        }
+        CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_descs.p + (uint64_t)s * max_frames, hd, nf * sizeof(czb_frame_desc), cudaMemcpyHostToDevice, ctx->copy_in));
+        CZB_CUDA(ctx, cudaEventRecord(ev_in[s], ctx->copy_in));
+        return CZS_OK;
+    };
+    if ((rc = enqueue_in(0))) return rc;
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const int s = (int)(c & 1);
+        const uint64_t f0 = cuts[c], f1 = cuts[c + 1], nf = f1 - f0;
+        if (c + 1 < n_chunks) {
+            // pin_b's descriptor half for slot s^1 is reused: its previous H2D (chunk c-1) has completed by now
+            // because chunk c-1's decode (which waited on it) was planned with a stream sync.
+            if ((rc = enqueue_in(c + 1))) return rc;
+        }
+        CZB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_in[s], 0));
+        if ((rc = czb_decode_batch_device(ctx, ctx->h_descs.p + (uint64_t)s * max_frames, ctx->h_results.p + (uint64_t)s * max_frames, nf,
+                                          flags, ctx->compute))) return rc;
+        CZB_CUDA(ctx, cudaEventRecord(ev_dec[s], ctx->compute));
+        CZB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_dec[s], 0));
+        const uint64_t db = dst_off[f0], dmis = db & 15;
+        CZB_CUDA(ctx, cudaMemcpyAsync(dst_base + db, ctx->h_dst[s].p + dmis, dst_off[f1] - db, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CZB_CUDA(ctx, cudaMemcpyAsync(results + f0, ctx->h_results.p + (uint64_t)s * max_frames, nf * sizeof(czb_frame_result),
+                                      cudaMemcpyDeviceToHost, ctx->copy_out));
+        CZB_CUDA(ctx, cudaEventRecord(ev_out[s], ctx->copy_out));
+    }
+    CZB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    CZB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    for (int s = 0; s < 2; s++) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_dec[s]); cudaEventDestroy(ev_out[s]); }
+    return CZS_OK;
+}
+
+// ---- header pre-pass (CPU only) ---------------------------------------------------------------
+extern "C" int czb_frame_header_info_host(const uint8_t* src, uint64_t src_len, czb_frame_header_info* out) {
+    if (!out || (!src && src_len)) return CZS_BAD_ARGUMENT;
+    memset(out, 0, sizeof *out);
+    FrameHeader fh{};
+    int32_t st = parse_frame_header(src, src_len, fh);
+    uint64_t ws = 0;
+    if (st == CZS_OK) st = frame_window_size(fh, false, ws);
+    out->status = st;
+    if (st != CZS_OK) return st;
+    out->header_len = fh.hdr_len; out->content_size = fh.fcs; out->window_size = ws;
+    out->fcs_present = fh.fcs_bytes != 0; out->has_checksum_flag = (fh.descriptor >> 2) & 1;
+    out->single_segment = (fh.descriptor >> 5) & 1; out->dict_id = fh.dict_id;
+    return CZS_OK;
+}
+
+extern "C" int czb_find_frame_end_host(const uint8_t* src, uint64_t src_len, uint64_t* frame_len) {
+    if (!frame_len || (!src && src_len)) return CZS_BAD_ARGUMENT;
+    *frame_len = 0;
+    FrameHeader fh{};
+    int32_t st = parse_frame_header(src, src_len, fh);
+    if (st != CZS_OK) return st;
+    uint64_t pos = fh.hdr_len;
+    for (;;) {
+        ParsedBlock pb;
+        parse_block_at(src, src_len, pos, pb);
+        if (pb.hdr_status != CZS_OK) return pb.hdr_status;
+        pos += 3 + pb.content;
+        if (pb.last) break;
+    }
+    if ((fh.descriptor >> 2) & 1) { if (src_len - pos < 4) return CZS_PANIC_TRUNCATED; pos += 4; }
+    *frame_len = pos;
+    return CZS_OK;
+}
+
+// ---- debug taps ---------------------------------------------------------------------------------
+extern "C" int czb_debug_last_wave_counts(czb_context* ctx, uint64_t* n_blocks, uint64_t* lit_bytes, uint64_t* n_seq) {
+    if (!ctx) return CZS_BAD_ARGUMENT;
+    if (n_blocks) *n_blocks = ctx->last_wave.n_blocks;
+    if (lit_bytes) *lit_bytes = ctx->last_wave.lit_bytes;
+    if (n_seq) *n_seq = ctx->last_wave.n_seq;
+    return CZS_OK;
+}
+extern "C" int czb_debug_copy_blocks(czb_context* ctx, czb_debug_block* out, uint64_t cap) {
+    if (!ctx || !out) return CZS_BAD_ARGUMENT;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CZB_CUDA(ctx, cudaDeviceSynchronize());
+    const uint64_t nb = std::min<uint64_t>(cap, ctx->last_wave.n_blocks);
+    std::vector<BlockDesc> h(nb);
+    if (nb) CZB_CUDA(ctx, cudaMemcpy(h.data(), ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < nb; i++) {
+        const BlockDesc& d = h[i];
+        czb_debug_block& o = out[i];
+        o.frame = d.frame; o.block_type = d.type; o.lit_type = d.lit_type; o.n_streams = d.n_streams; o.modes = d.modes;
+        o.regen_size = d.regen; o.n_seq = d.n_seq; o.lit_off = d.lit_off; o.seq_off = d.seq_off;
+        int32_t st = d.pre_status;
+        if (st == CZS_OK && d.type == BT_COMPRESSED) {
+            if (d.lit_type >= LT_COMPRESSED && d.huf_status != CZS_OK) st = d.huf_status;
+            else if (d.seqhdr_status != CZS_OK) st = d.seqhdr_status;
+            else if (d.n_seq && d.fse_status != CZS_OK) st = d.fse_status;
+        }
+        o.status = st;
+    }
+    return CZS_OK;
+}
+extern "C" int czb_debug_copy_literals(czb_context* ctx, uint8_t* out, uint64_t cap) {
+    if (!ctx || !out) return CZS_BAD_ARGUMENT;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CZB_CUDA(ctx, cudaDeviceSynchronize());
+    const uint64_t nbytes = std::min<uint64_t>(cap, ctx->last_wave.lit_bytes);
+    if (nbytes) CZB_CUDA(ctx, cudaMemcpy(out, ctx->lit.p, nbytes, cudaMemcpyDeviceToHost));
+    return CZS_OK;
+}
+extern "C" int czb_debug_copy_sequences(czb_context* ctx, uint32_t* out, uint64_t cap_seqs) {
+    if (!ctx || !out) return CZS_BAD_ARGUMENT;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CZB_CUDA(ctx, cudaDeviceSynchronize());
+    const uint64_t ns = std::min<uint64_t>(cap_seqs, ctx->last_wave.n_seq);
+    if (ns) CZB_CUDA(ctx, cudaMemcpy(out, ctx->seq.p, ns * sizeof(Seq), cudaMemcpyDeviceToHost));
+    return CZS_OK;
+}
+
+extern "C" const char* czs_status_name(int s) {
+    switch (s) {
+#define N(x) case x: return #x;
+        N(CZS_OK) N(CZS_MAGIC_NUMBER_READ_ERROR) N(CZS_FRAME_DESCRIPTOR_READ_ERROR) N(CZS_DICTIONARY_ID_READ_ERROR)
+        N(CZS_WINDOW_DESCRIPTOR_READ_ERROR) N(CZS_BAD_MAGIC_NUMBER) N(CZS_SKIP_FRAME) N(CZS_WINDOW_TOO_BIG) N(CZS_WINDOW_TOO_SMALL)
+        N(CZS_WINDOW_SIZE_TOO_BIG) N(CZS_FOUND_RESERVED_BLOCK) N(CZS_BLOCK_SIZE_TOO_LARGE) N(CZS_MALFORMED_SECTION_HEADER)
+        N(CZS_LIT_GET_BITS_ERROR) N(CZS_LIT_NOT_ENOUGH_BYTES) N(CZS_SEQ_HDR_NOT_ENOUGH_BYTES) N(CZS_MISSING_BYTES_FOR_JUMP_HEADER)
+        N(CZS_MISSING_BYTES_FOR_LITERALS) N(CZS_LIT_EXTRA_PADDING) N(CZS_BITSTREAM_READ_MISMATCH) N(CZS_DECODED_LITERAL_COUNT_MISMATCH)
+        N(CZS_UNINITIALIZED_HUFFMAN_TABLE) N(CZS_HUF_SOURCE_IS_EMPTY) N(CZS_HUF_NOT_ENOUGH_BYTES_FOR_WEIGHTS) N(CZS_HUF_EXTRA_PADDING)
+        N(CZS_HUF_TOO_MANY_WEIGHTS) N(CZS_HUF_MISSING_WEIGHTS) N(CZS_HUF_LEFTOVER_NOT_POWER_OF_2)
+        N(CZS_HUF_NOT_ENOUGH_BYTES_TO_DECOMPRESS_WEIGHTS) N(CZS_HUF_FSE_TABLE_USED_TOO_MANY_BYTES) N(CZS_HUF_NOT_ENOUGH_BYTES_IN_SOURCE)
+        N(CZS_HUF_WEIGHT_BIGGER_THAN_MAX_NUM_BITS) N(CZS_HUF_MAX_BITS_TOO_HIGH) N(CZS_FSE_ACC_LOG_IS_ZERO) N(CZS_FSE_ACC_LOG_TOO_BIG)
+        N(CZS_FSE_PROBABILITY_COUNTER_MISMATCH) N(CZS_FSE_TOO_MANY_SYMBOLS) N(CZS_FSE_GET_BITS_ERROR) N(CZS_FSE_TABLE_IS_UNINITIALIZED)
+        N(CZS_SEQ_EXTRA_PADDING) N(CZS_SEQ_UNSUPPORTED_OFFSET) N(CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES) N(CZS_SEQ_EXTRA_BITS)
+        N(CZS_SEQ_GET_BITS_ERROR) N(CZS_MISSING_BYTE_FOR_RLE_LL_TABLE) N(CZS_MISSING_BYTE_FOR_RLE_OF_TABLE)
+        N(CZS_MISSING_BYTE_FOR_RLE_ML_TABLE) N(CZS_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE) N(CZS_EXEC_ZERO_OFFSET)
+        N(CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY) N(CZS_OFFSET_TOO_BIG) N(CZS_PANIC_TRUNCATED) N(CZS_PANIC_INTERNAL) N(CZS_DST_TOO_SMALL)
+        N(CZS_UNSUPPORTED) N(CZS_CUDA_ERROR) N(CZS_BAD_ARGUMENT) N(CZS_NOT_DECODED)
+#undef N
+    }
+    return "CZS_UNKNOWN";
+}

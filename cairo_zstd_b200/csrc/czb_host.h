@@ -1,0 +1,47 @@
+// czb_host.h -- host-side context shared by czb_api.cu and czb_handle.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "czb_internal.cuh"
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    uint64_t cap = 0;  // elements
+};
+
+constexpr uint64_t kMaxWaves = 4096;
+
+struct czb_context {
+    int device = 0;
+    uint64_t budget = 0;        // soft cap on per-wave scratch bytes
+    uint64_t wave_frames = 0;   // upper bound on frames per wave
+    uint64_t host_chunk_bytes = 3ull << 30;  // src+dst bytes per chunk of the packed host path
+    std::string last_error;
+    uint64_t launches = 0;
+
+    // decode workspace (device)
+    DevBuf<czb::FrameInfo> infos;
+    DevBuf<czb::WaveTotals> totals_d;
+    czb::WaveTotals* totals_h = nullptr;  // pinned
+    DevBuf<czb::WaveCounters> counters;
+    DevBuf<czb::BlockDesc> blocks;
+    DevBuf<uint32_t> huf_items, fse_items;
+    DevBuf<uint8_t> lit;
+    DevBuf<czb::Seq> seq;
+
+    // staging for the host-pointer entry points
+    DevBuf<uint8_t> h_src[2], h_dst[2];
+    DevBuf<czb_frame_desc> h_descs;
+    DevBuf<czb_frame_result> h_results;
+    uint8_t* pin_a = nullptr; uint64_t pin_a_cap = 0;
+    uint8_t* pin_b = nullptr; uint64_t pin_b_cap = 0;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr, compute = nullptr;
+
+    // debug taps
+    czb::WaveTotals last_wave{};
+    uint64_t last_wave_first = 0, last_wave_count = 0;
+};

@@ -1,0 +1,275 @@
+// k_fse.cu -- sequence section decode: FSE tables in shared memory, one lane per block.
+//
+// Reference path: decode_sequences, maybe_update_fse_tables, decode_sequences_{with,without}_rle,
+// lookup_ll_code / lookup_ml_code (src/decoding/sequence_section_decoder.cairo:35-647),
+// FSETable / FSEDecoder (src/fse/fse_decoder.cairo:64-400), BitReaderReversed
+// (src/decoding/bit_reader_reverse.cairo), and do_offset_history
+// (src/decoding/sequence_execution.cairo:85-129), which is folded in here because it is a serial
+// chain over the same sequences.
+//
+// Mapping: the interleaved LL/OF/ML state machine is one dependency chain per block and cannot be
+// split, so parallelism comes from blocks: a CTA owns 32 blocks, all 8 warps build the 96 tables
+// cooperatively, then warp 0 decodes with lane = block.  Throughput is bounded by
+// (blocks resident per SM) / (chain latency per sequence); 16-bit table entries (czb_fse_build.cuh)
+// keep a block's three tables at <= 2.5 KiB so 64 blocks fit per SM.  HBM traffic: the bitstream in
+// (a few bytes per sequence) and 12 B per sequence out to scratch.
+#include "czb_fse_build.cuh"
+#include "czb_internal.cuh"
+
+namespace czb {
+
+constexpr int FSE_WARPS = 8;
+constexpr int FSE_SLOTS = 32;
+constexpr int FSE_SLOT_ENTRIES = 512 + 512 + 256;  // LL (log<=9), ML (log<=9), OF (log<=8)
+constexpr int FSE_LL_OFS = 0, FSE_ML_OFS = 512, FSE_OF_OFS = 1024;
+
+struct FseSlot {
+    const uint8_t* bits;   // sequence bitstream
+    Seq* out;
+    uint32_t bits_len;
+    uint32_t n_seq;
+    uint32_t blk;
+    int32_t status;
+    uint16_t tbl[3];       // LL, OF, ML: entry index of the table inside FseSmem::entries (flat)
+    int8_t log[3];         // accuracy log; 0 = RLE (one entry); -1 = never initialised
+    uint8_t first_in_frame;
+    uint8_t any_rle;
+};
+
+struct FseWarpTmp {
+    int16_t probs[FSE_MAX_SYMBOLS];
+    uint8_t rank_sym[1 << FSE_MAX_LOG];
+};
+
+struct FseSmem {
+    uint16_t entries[FSE_SLOTS * FSE_SLOT_ENTRIES + 64 + 32 + 64];  // per-slot tables, then predefined LL, OF, ML
+    FseSlot slot[FSE_SLOTS];
+    FseWarpTmp tmp[FSE_WARPS];
+    uint32_t ll_code[36];  // base | bits << 20 (lookup_ll_code :299-345)
+    uint32_t ml_code[53];  // (lookup_ml_code :347-395)
+};
+constexpr int FSE_PREDEF_LL = FSE_SLOTS * FSE_SLOT_ENTRIES, FSE_PREDEF_OF = FSE_PREDEF_LL + 64, FSE_PREDEF_ML = FSE_PREDEF_OF + 32;
+
+__device__ __constant__ uint32_t kLLBase[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536};
+__device__ __constant__ uint8_t kLLBits[36] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+__device__ __constant__ uint32_t kMLBase[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539};
+__device__ __constant__ uint8_t kMLBits[53] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16};
+
+__device__ __forceinline__ int stream_max_log(int s) { return s == 1 ? 8 : 9; }  // LL 9, OF 8, ML 9 (:397-399)
+
+// Bytes a table description of `mode` occupies at p (for skipping to a later stream's description).
+// Lane 0 only.  Returns false if the description cannot be parsed.
+__device__ inline bool skip_description(int mode, int s, const uint8_t* p, int len, FseWarpTmp& t, int& bytes) {
+    bytes = 0;
+    if (mode == MODE_RLE) { if (len < 1) return false; bytes = 1; return true; }
+    if (mode == MODE_FSE) {
+        int n_probs, log;
+        return fse_read_probabilities(p, len, stream_max_log(s), t.probs, n_probs, log, bytes) == CZS_OK;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(FSE_WARPS * 32) k_fse(const czb_frame_desc* __restrict__ descs, BlockDesc* __restrict__ blocks,
+                                                         const uint32_t* __restrict__ items,
+                                                         const WaveCounters* __restrict__ counters, Seq* __restrict__ seq_scratch) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    FseSmem& sm = *reinterpret_cast<FseSmem*>(smem_raw);
+    const uint32_t n_items = counters->n_fse;
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t first = blockIdx.x * FSE_SLOTS;
+    if (first >= n_items) return;  // whole CTA
+    FseWarpTmp& tmp = sm.tmp[warp];
+
+    // ---- predefined tables and code tables, once per CTA ----
+    if (warp < 3) {
+        const int n = warp == 0 ? 36 : (warp == 1 ? 29 : 53);
+        const int8_t* src = warp == 0 ? kLLDefault : (warp == 1 ? kOFDefault : kMLDefault);
+        for (int i = lane; i < n; i += 32) tmp.probs[i] = src[i];
+        __syncwarp();
+        fse_build_table_warp(tmp.probs, n, warp == 1 ? 5 : 6,
+                             sm.entries + (warp == 0 ? FSE_PREDEF_LL : (warp == 1 ? FSE_PREDEF_OF : FSE_PREDEF_ML)), tmp.rank_sym);
+    } else if (warp == 3) {
+        for (int i = lane; i < 36; i += 32) sm.ll_code[i] = kLLBase[i] | ((uint32_t)kLLBits[i] << 20);
+        for (int i = lane; i < 53; i += 32) sm.ml_code[i] = kMLBase[i] | ((uint32_t)kMLBits[i] << 20);
+    }
+    __syncwarp();
+
+    // ---- phase 1: maybe_update_fse_tables per block (:405-647), one block per warp at a time ----
+    for (int s = warp; s < FSE_SLOTS; s += FSE_WARPS) {
+        FseSlot& sl = sm.slot[s];
+        const uint32_t item = first + s;
+        if (item >= n_items) { if (lane == 0) { sl.status = CZS_NOT_DECODED; sl.blk = NONE32; sl.n_seq = 0; } continue; }
+        const uint32_t bi = items[item];
+        const BlockDesc d = blocks[bi];
+        const uint8_t* fsrc = descs[d.frame].src;
+        const uint32_t modes[3] = {(uint32_t)d.modes >> 6, ((uint32_t)d.modes >> 4) & 3u, ((uint32_t)d.modes >> 2) & 3u};
+        uint32_t cursor = d.seq_src_off;
+        const uint32_t end = d.seq_src_off + d.seq_src_len;
+        int32_t st = CZS_OK;
+        bool any_rle = false;
+        const int region[3] = {s * FSE_SLOT_ENTRIES + FSE_LL_OFS, s * FSE_SLOT_ENTRIES + FSE_OF_OFS, s * FSE_SLOT_ENTRIES + FSE_ML_OFS};
+        const int predef[3] = {FSE_PREDEF_LL, FSE_PREDEF_OF, FSE_PREDEF_ML};
+        const int predef_log[3] = {6, 5, 6};
+        for (int k = 0; k < 3 && st == CZS_OK; k++) {
+            uint32_t mode = modes[k];
+            const uint8_t* p = fsrc + cursor;
+            int plen = (int)(end - cursor);
+            const bool own = mode != MODE_REPEAT;
+            bool usable = true;
+            if (!own) {  // Repeat: re-derive the table from the block that last set it
+                const uint32_t sb = d.tbl_src_blk[k];
+                if (sb == NONE32) { usable = false; if (lane == 0) { sl.log[k] = -1; sl.tbl[k] = (uint16_t)region[k]; } }
+                else {
+                    const BlockDesc sd = blocks[sb];
+                    const uint8_t* ssrc = fsrc;  // same frame
+                    const uint32_t sm3[3] = {(uint32_t)sd.modes >> 6, ((uint32_t)sd.modes >> 4) & 3u, ((uint32_t)sd.modes >> 2) & 3u};
+                    uint32_t scur = sd.seq_src_off;
+                    const uint32_t send = sd.seq_src_off + sd.seq_src_len;
+                    int ok = 1;
+                    if (lane == 0) {
+                        for (int q = 0; q < k && ok; q++) {
+                            int bytes = 0;
+                            ok = skip_description((int)sm3[q], q, ssrc + scur, (int)(send - scur), tmp, bytes) ? 1 : 0;
+                            scur += (uint32_t)bytes;
+                        }
+                    }
+                    ok = __shfl_sync(0xFFFFFFFFu, ok, 0);
+                    scur = __shfl_sync(0xFFFFFFFFu, scur, 0);
+                    if (!ok) { usable = false; if (lane == 0) { sl.log[k] = -1; sl.tbl[k] = (uint16_t)region[k]; } }  // source block failed the frame earlier
+                    mode = sm3[k];
+                    p = ssrc + scur;
+                    plen = (int)(send - scur);
+                }
+            }
+            if (!usable) continue;
+            if (mode == MODE_PREDEFINED) {
+                if (lane == 0) { sl.tbl[k] = (uint16_t)predef[k]; sl.log[k] = (int8_t)predef_log[k]; }
+            } else if (mode == MODE_RLE) {
+                if (plen < 1) {
+                    if (own) st = k == 0 ? CZS_MISSING_BYTE_FOR_RLE_LL_TABLE : (k == 1 ? CZS_MISSING_BYTE_FOR_RLE_OF_TABLE : CZS_MISSING_BYTE_FOR_RLE_ML_TABLE);
+                    else if (lane == 0) { sl.log[k] = -1; sl.tbl[k] = (uint16_t)region[k]; }
+                } else {
+                    if (lane == 0) { sm.entries[region[k]] = fse_entry(p[0], 1u); sl.tbl[k] = (uint16_t)region[k]; sl.log[k] = 0; }
+                    any_rle = true;
+                    if (own) cursor += 1;
+                }
+            } else {  // MODE_FSE
+                int n_probs = 0, log = 0, used = 0;
+                int32_t pst = CZS_OK;
+                if (lane == 0) pst = fse_read_probabilities(p, plen, stream_max_log(k), tmp.probs, n_probs, log, used);
+                pst = __shfl_sync(0xFFFFFFFFu, pst, 0);
+                n_probs = __shfl_sync(0xFFFFFFFFu, n_probs, 0);
+                log = __shfl_sync(0xFFFFFFFFu, log, 0);
+                used = __shfl_sync(0xFFFFFFFFu, used, 0);
+                __syncwarp();
+                if (pst != CZS_OK) {
+                    if (own) st = pst;
+                    else if (lane == 0) { sl.log[k] = -1; sl.tbl[k] = (uint16_t)region[k]; }
+                } else {
+                    fse_build_table_warp(tmp.probs, n_probs, log, sm.entries + region[k], tmp.rank_sym);
+                    if (lane == 0) { sl.tbl[k] = (uint16_t)region[k]; sl.log[k] = (int8_t)log; }
+                    if (own) cursor += (uint32_t)used;
+                }
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            sl.blk = bi; sl.n_seq = d.n_seq; sl.status = st;
+            sl.bits = fsrc + cursor; sl.bits_len = end - cursor;
+            sl.out = seq_scratch + d.seq_off;
+            sl.first_in_frame = d.first_in_frame; sl.any_rle = any_rle ? 1 : 0;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp != 0) return;
+
+    // ---- phase 2: lane = block ----
+    const FseSlot& sl = sm.slot[lane];
+    if (sl.blk == NONE32) return;
+    int32_t st = sl.status;
+    uint32_t h0, h1, h2;
+    if (sl.first_in_frame) { h0 = 1; h1 = 4; h2 = 8; }  // scratch.cairo:35
+    else { h0 = sym_enc(0); h1 = sym_enc(1); h2 = sym_enc(2); }
+    if (st == CZS_OK) {
+        RevBits br;
+        if (!br.init(sl.bits, (int)sl.bits_len)) st = CZS_SEQ_EXTRA_PADDING;  // :46-64
+        else if (sl.log[0] < 0 || sl.log[1] < 0 || sl.log[2] < 0) st = CZS_FSE_TABLE_IS_UNINITIALIZED;  // fse_decoder.cairo:82-84
+        else {
+            const uint32_t logLL = (uint32_t)sl.log[0], logOF = (uint32_t)sl.log[1], logML = (uint32_t)sl.log[2];
+            const uint16_t* tLL = sm.entries + sl.tbl[0];
+            const uint16_t* tOF = sm.entries + sl.tbl[1];
+            const uint16_t* tML = sm.entries + sl.tbl[2];
+            // init order LL, OF, ML (:207-218)
+            uint32_t eLL = tLL[br.get((int)logLL)];
+            uint32_t eOF = tOF[br.get((int)logOF)];
+            uint32_t eML = tML[br.get((int)logML)];
+            const uint32_t n_seq = sl.n_seq;
+            Seq* out = sl.out;
+            for (uint32_t i = 0; i < n_seq; i++) {  // hot loop :223-286
+                if (br.avail <= 32) br.refill();
+                const uint32_t llc = fse_entry_sym(eLL), mlc = fse_entry_sym(eML), ofc = fse_entry_sym(eOF);
+                if (ofc >= 32) { st = CZS_SEQ_UNSUPPORTED_OFFSET; break; }       // :235-237
+                if (mlc > 52 || llc > 35) { st = CZS_SEQ_GET_BITS_ERROR; break; }  // (0,255) -> TooManyBits
+                const uint32_t lle = sm.ll_code[llc], mle = sm.ml_code[mlc];
+                const int llb = (int)(lle >> 20), mlb = (int)(mle >> 20);
+                uint32_t ofv, mlv, llv;
+                if ((int)ofc + mlb + llb <= br.avail) {  // read order OF, ML, LL (:239)
+                    ofv = br.get((int)ofc); mlv = br.get(mlb); llv = br.get(llb);
+                } else {
+                    ofv = br.get((int)ofc);
+                    if (br.avail <= 32) br.refill();
+                    mlv = br.get(mlb); llv = br.get(llb);
+                }
+                const uint32_t v = (1u << ofc) + ofv;  // :243
+                const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
+                // do_offset_history (sequence_execution.cairo:85-129)
+                uint32_t act;
+                if (ll > 0) {
+                    if (v == 1) act = h0;
+                    else if (v == 2) { act = h1; h1 = h0; h0 = act; }
+                    else if (v == 3) { act = h2; h2 = h1; h1 = h0; h0 = act; }
+                    else { act = v - 3; if (act >= SYM_BASE) act = REAL_OFF_CLAMP; h2 = h1; h1 = h0; h0 = act; }
+                } else {
+                    if (v == 1) { act = h1; h1 = h0; h0 = act; }
+                    else if (v == 2) { act = h2; h2 = h1; h1 = h0; h0 = act; }
+                    else if (v == 3) { act = h0 - 1; h2 = h1; h1 = h0; h0 = act; }
+                    else { act = v - 3; if (act >= SYM_BASE) act = REAL_OFF_CLAMP; h2 = h1; h1 = h0; h0 = act; }
+                }
+                out[i].ll = ll; out[i].ml = ml; out[i].off = act;
+                if (i + 1 < n_seq) {  // update order LL, ML, OF (:258-276)
+                    if (br.avail <= 32) br.refill();
+                    const uint32_t nbLL = fse_entry_nbits(eLL, logLL), nbML = fse_entry_nbits(eML, logML), nbOF = fse_entry_nbits(eOF, logOF);
+                    const uint32_t sLL = fse_entry_base(eLL, nbLL, logLL) + br.get((int)nbLL);
+                    const uint32_t sML = fse_entry_base(eML, nbML, logML) + br.get((int)nbML);
+                    const uint32_t sOF = fse_entry_base(eOF, nbOF, logOF) + br.get((int)nbOF);
+                    eLL = tLL[sLL & ((1u << logLL) - 1u)];
+                    eML = tML[sML & ((1u << logML) - 1u)];
+                    eOF = tOF[sOF & ((1u << logOF) - 1u)];
+                }
+                if (br.rem < 0) {  // :281-283; the no-RLE variant traps on the unwrap at :279 instead
+                    st = sl.any_rle ? CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES : CZS_PANIC_INTERNAL;
+                    break;
+                }
+            }
+            if (st == CZS_OK && br.rem > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
+        }
+    }
+    BlockDesc& d = blocks[sl.blk];
+    d.fse_status = st;
+    d.hist_out[0] = h0; d.hist_out[1] = h1; d.hist_out[2] = h2;
+}
+
+void launch_fse(const LaunchCtx& lc, const czb_frame_desc* descs, BlockDesc* blocks, const uint32_t* items,
+                const WaveCounters* counters, uint32_t max_items, Seq* seq_scratch) {
+    if (!max_items) return;
+    const unsigned grid = (max_items + FSE_SLOTS - 1) / FSE_SLOTS;
+    k_fse<<<grid, FSE_WARPS * 32, sizeof(FseSmem), lc.stream>>>(descs, blocks, items, counters, seq_scratch);
+    ++*lc.launches;
+}
+
+int setup_fse_attributes() {
+    return (int)cudaFuncSetAttribute(k_fse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FseSmem));
+}
+
+}  // namespace czb

@@ -1,0 +1,244 @@
+// k_scan.cu -- frame/block header scan and work-list construction (thread per frame).
+//
+// Reference path: read_frame_header (src/frame.cairo:152-284), FrameDecoderStateTrait::new
+// (src/frame_decoder.cairo:54-76), the block loop of decode_blocks (:156-222) as far as the
+// headers go, read_block_header (src/decoding/block_decoder.cairo:237-278) and the section
+// headers (src/blocks/literals_section.cairo:81-175, src/blocks/sequence_section.cairo:77-114).
+//
+// Roofline: negligible traffic (a few bytes per block); latency-bound pointer chasing, one
+// dependent load per block.  Frames are independent, so one thread per frame.
+#include "czb_internal.cuh"
+#include "czb_parse.cuh"
+
+namespace czb {
+
+__device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// Reserve `n` units for this lane from a shared counter: one atomic per warp.
+template <typename T>
+__device__ __forceinline__ T warp_reserve(T* counter, T n) {
+    const unsigned lane = lane_id();
+    T incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= (unsigned)o) incl += t;
+    }
+    T total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    T base = 0;
+    if (lane == 0 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + incl - n;
+}
+
+struct Walk {
+    uint32_t n_blocks, n_huf, n_fse;
+    uint64_t lit_bytes, n_seq, src_end;
+    uint32_t checksum;
+    uint8_t has_checksum;
+};
+
+__device__ __forceinline__ uint64_t align16(uint64_t v) { return (v + 15) & ~15ull; }
+
+__global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __restrict__ descs, FrameInfo* __restrict__ infos,
+                                                      uint64_t n, uint64_t wave_frames, WaveTotals* __restrict__ totals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    FrameInfo fi;
+    memset(&fi, 0, sizeof fi);
+    uint64_t src_bytes = 0;
+    if (i < n) {
+        const uint8_t* src = descs[i].src;
+        uint64_t len = descs[i].src_len;
+        if (len > 0xFFFFFFF0ull) len = 0xFFFFFFF0ull;
+        FrameHeader fh;
+        int32_t st = parse_frame_header(src, len, fh);
+        uint64_t ws = 0;
+        if (st == CZS_OK) st = frame_window_size(fh, false, ws);
+        fi.status = st;
+        if (st == CZS_OK) {
+            fi.hdr_len = fh.hdr_len; fi.fcs = fh.fcs; fi.window = ws; fi.descriptor = fh.descriptor;
+            uint64_t pos = fh.hdr_len;
+            for (;;) {
+                ParsedBlock pb;
+                parse_block_at(src, len, pos, pb);
+                fi.n_blocks++;
+                if (pb.hdr_status != CZS_OK) break;
+                if (pb.type == BT_COMPRESSED && pb.pre_status == CZS_OK) {
+                    if (pb.lit_type >= LT_COMPRESSED) { fi.n_huf++; fi.lit_bytes += align16((uint64_t)pb.regen + 16); }
+                    if (pb.seqhdr_status == CZS_OK && pb.n_seq) { fi.n_fse++; fi.n_seq += pb.n_seq; }
+                }
+                pos += 3 + pb.content;
+                if (pb.last) {
+                    if ((fh.descriptor >> 2) & 1) {
+                        if (len - pos < 4) { fi.n_blocks++; break; }  // pseudo block: source.slice(0,4) traps, frame_decoder.cairo:190
+                        fi.checksum = (uint32_t)src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16) | ((uint32_t)src[pos + 3] << 24);
+                        fi.has_checksum = 1;
+                        pos += 4;
+                    }
+                    fi.src_end = pos;
+                    break;
+                }
+            }
+            src_bytes = pos;
+        }
+        infos[i] = fi;
+    }
+    // per-wave totals: a warp never straddles waves (wave_frames is a multiple of 128)
+    unsigned long long nb = warp_sum_ull(fi.n_blocks), lb = warp_sum_ull(fi.lit_bytes), ns = warp_sum_ull(fi.n_seq);
+    unsigned long long nh = warp_sum_ull(fi.n_huf), nf = warp_sum_ull(fi.n_fse), sb = warp_sum_ull(src_bytes);
+    if (lane_id() == 0 && i < n) {
+        WaveTotals* t = totals + i / wave_frames;
+        if (nb) atomicAdd(&t->n_blocks, nb);
+        if (lb) atomicAdd(&t->lit_bytes, lb);
+        if (ns) atomicAdd(&t->n_seq, ns);
+        if (nh) atomicAdd(&t->n_huf, nh);
+        if (nf) atomicAdd(&t->n_fse, nf);
+        if (sb) atomicAdd(&t->src_bytes, sb);
+    }
+}
+
+// Recompute per-wave totals for a different wave size (planning retry; infos already scanned).
+__global__ void __launch_bounds__(128) k_wave_totals(const FrameInfo* __restrict__ infos, uint64_t n, uint64_t wave_frames,
+                                                      WaveTotals* __restrict__ totals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long nb = 0, lb = 0, ns = 0, nh = 0, nf = 0;
+    if (i < n) { const FrameInfo& fi = infos[i]; nb = fi.n_blocks; lb = fi.lit_bytes; ns = fi.n_seq; nh = fi.n_huf; nf = fi.n_fse; }
+    nb = warp_sum_ull(nb); lb = warp_sum_ull(lb); ns = warp_sum_ull(ns); nh = warp_sum_ull(nh); nf = warp_sum_ull(nf);
+    if (lane_id() == 0 && i < n) {
+        WaveTotals* t = totals + i / wave_frames;
+        if (nb) atomicAdd(&t->n_blocks, nb);
+        if (lb) atomicAdd(&t->lit_bytes, lb);
+        if (ns) atomicAdd(&t->n_seq, ns);
+        if (nh) atomicAdd(&t->n_huf, nh);
+        if (nf) atomicAdd(&t->n_fse, nf);
+    }
+}
+
+// Second walk: write one BlockDesc per block, resolve the table-reuse chains
+// (Treeless literals: literals_section_decoder.cairo:82-86; Repeat modes:
+// sequence_section_decoder.cairo:483, :551, :643) and append the entropy work items.
+__global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __restrict__ descs, FrameInfo* __restrict__ infos,
+                                                      uint64_t first, uint64_t count, BlockDesc* __restrict__ blocks,
+                                                      uint32_t* __restrict__ huf_items, uint32_t* __restrict__ fse_items,
+                                                      WaveCounters* __restrict__ ctr) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < count;
+    const uint64_t i = first + (active ? t : 0);
+    FrameInfo fi;
+    if (active) fi = infos[i]; else memset(&fi, 0, sizeof fi);
+    const bool walk = active && fi.status == CZS_OK;
+    unsigned long long blk_base = warp_reserve<unsigned long long>(&ctr->n_blocks, walk ? fi.n_blocks : 0);
+    unsigned long long lit_base = warp_reserve<unsigned long long>(&ctr->lit_bytes, walk ? fi.lit_bytes : 0);
+    unsigned long long seq_base = warp_reserve<unsigned long long>(&ctr->n_seq, walk ? fi.n_seq : 0);
+    unsigned int huf_base = warp_reserve<unsigned int>(&ctr->n_huf, walk ? fi.n_huf : 0);
+    unsigned int fse_base = warp_reserve<unsigned int>(&ctr->n_fse, walk ? fi.n_fse : 0);
+    if (!active) return;
+    infos[i].block_base = (uint32_t)blk_base;
+    if (!walk) return;
+
+    const uint8_t* src = descs[i].src;
+    uint64_t len = descs[i].src_len;
+    if (len > 0xFFFFFFF0ull) len = 0xFFFFFFF0ull;
+    uint64_t pos = fi.hdr_len;
+    uint32_t bidx = (uint32_t)blk_base;
+    uint32_t last_huf = NONE32, last_tbl[3] = {NONE32, NONE32, NONE32};
+    bool seen_seq = false;
+    for (uint32_t k = 0; k < fi.n_blocks; k++, bidx++) {
+        BlockDesc d;
+        memset(&d, 0, sizeof d);
+        d.frame = (uint32_t)(i - first);
+        d.huf_src_blk = NONE32; d.tbl_src_blk[0] = d.tbl_src_blk[1] = d.tbl_src_blk[2] = NONE32;
+        d.huf_status = CZS_OK; d.fse_status = CZS_OK;
+        if (pos == ~0ull) {  // pseudo block for the missing checksum trailer
+            d.type = BT_ERROR; d.pre_status = CZS_PANIC_TRUNCATED;
+            blocks[bidx] = d;
+            break;
+        }
+        ParsedBlock pb;
+        parse_block_at(src, len, pos, pb);
+        d.src_off = (uint32_t)(pos + 3);
+        d.size = pb.size; d.type = pb.type; d.last = pb.last;
+        if (pb.hdr_status != CZS_OK) {
+            d.type = BT_ERROR; d.pre_status = pb.hdr_status;
+            blocks[bidx] = d;
+            break;
+        }
+        if (pb.type == BT_COMPRESSED) {
+            d.pre_status = pb.pre_status; d.seqhdr_status = pb.seqhdr_status;
+            d.lit_type = pb.lit_type; d.n_streams = pb.n_streams; d.regen = pb.regen;
+            d.lit_src_off = d.src_off + pb.lit_hdr; d.lit_comp = pb.lit_payload;
+            if (pb.pre_status == CZS_OK) {
+                if (pb.lit_type >= LT_COMPRESSED) {
+                    if (pb.lit_type == LT_COMPRESSED) last_huf = bidx;
+                    d.huf_src_blk = last_huf;
+                    d.lit_off = lit_base; lit_base += align16((uint64_t)pb.regen + 16);
+                    huf_items[huf_base++] = bidx;
+                }
+                if (pb.seqhdr_status == CZS_OK) {
+                    d.n_seq = pb.n_seq; d.modes = pb.modes;
+                    d.seq_src_off = d.lit_src_off + pb.lit_payload + pb.seq_hdr;
+                    d.seq_src_len = d.src_off + pb.size - d.seq_src_off;
+                    if (pb.n_seq) {
+                        const uint32_t m[3] = {(uint32_t)pb.modes >> 6, ((uint32_t)pb.modes >> 4) & 3u, ((uint32_t)pb.modes >> 2) & 3u};
+#pragma unroll
+                        for (int s = 0; s < 3; s++) {
+                            if (m[s] != MODE_REPEAT) last_tbl[s] = bidx;
+                            d.tbl_src_blk[s] = last_tbl[s];
+                        }
+                        d.first_in_frame = seen_seq ? 0 : 1;
+                        seen_seq = true;
+                        d.seq_off = seq_base; seq_base += pb.n_seq;
+                        fse_items[fse_base++] = bidx;
+                    }
+                }
+            }
+        }
+        blocks[bidx] = d;
+        pos += 3 + pb.content;
+        if (pb.last) pos = ~0ull;  // only reached again if the scan counted a trailer pseudo block
+    }
+}
+
+// Frames whose header failed never reach k_exec's block loop; give every frame its
+// header-level result first (k_exec overwrites the rest).
+__global__ void __launch_bounds__(256) k_header_results(const FrameInfo* __restrict__ infos, czb_frame_result* __restrict__ results, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FrameInfo fi = infos[i];
+    czb_frame_result r;
+    memset(&r, 0, sizeof r);
+    r.status = fi.status;
+    r.content_size = fi.fcs; r.window_size = fi.window;
+    results[i] = r;
+}
+
+void launch_scan_frames(const LaunchCtx& lc, const czb_frame_desc* descs, FrameInfo* infos, uint64_t n, uint64_t wave_frames,
+                        WaveTotals* totals) {
+    if (!n) return;
+    k_scan_frames<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(descs, infos, n, wave_frames, totals);
+    ++*lc.launches;
+}
+void launch_wave_totals(const LaunchCtx& lc, const FrameInfo* infos, uint64_t n, uint64_t wave_frames, WaveTotals* totals,
+                        uint64_t n_waves) {
+    if (!n) return;
+    cudaMemsetAsync(totals, 0, n_waves * sizeof(WaveTotals), lc.stream);
+    k_wave_totals<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(infos, n, wave_frames, totals);
+    ++*lc.launches;
+}
+void launch_fill_blocks(const LaunchCtx& lc, const czb_frame_desc* descs, FrameInfo* infos, uint64_t first, uint64_t count,
+                        BlockDesc* blocks, uint32_t* huf_items, uint32_t* fse_items, WaveCounters* counters) {
+    if (!count) return;
+    k_fill_blocks<<<(unsigned)((count + 127) / 128), 128, 0, lc.stream>>>(descs, infos, first, count, blocks, huf_items, fse_items, counters);
+    ++*lc.launches;
+}
+void launch_header_results(const LaunchCtx& lc, const FrameInfo* infos, czb_frame_result* results, uint64_t n) {
+    if (!n) return;
+    k_header_results<<<(unsigned)((n + 255) / 256), 256, 0, lc.stream>>>(infos, results, n);
+    ++*lc.launches;
+}
+
+}  // namespace czb
