@@ -66,7 +66,7 @@ EXPORTS = [
     "czb_fd_decode_from_to", "czb_fd_read", "czb_fd_content_size", "czb_fd_get_checksum_from_data",
     "czb_fd_get_calculated_checksum", "czb_fd_bytes_read_from_source", "czb_fd_is_finished", "czb_fd_blocks_decoded",
     "czb_debug_last_wave_counts", "czb_debug_copy_blocks", "czb_debug_copy_literals", "czb_debug_copy_sequences",
-    "czb_kernel_launches", "czs_status_name",
+    "czb_kernel_launches", "czb_profile_enable", "czb_profile_collect", "czs_status_name",
 ]
 
 _lib = None
@@ -118,6 +118,8 @@ def load_library():
     L.czb_debug_copy_sequences.argtypes = [vp, vp, u64]
     L.czb_kernel_launches.argtypes = [vp]
     L.czb_kernel_launches.restype = u64
+    L.czb_profile_enable.argtypes = [vp, C.c_int]
+    L.czb_profile_collect.argtypes = [vp, P(C.c_double), P(u64)]
     L.czs_status_name.argtypes = [C.c_int]
     L.czs_status_name.restype = C.c_char_p
     _lib = L
@@ -202,6 +204,19 @@ class Context:
         so = src_off.ctypes.data if hasattr(src_off, "ctypes") else C.addressof(src_off)
         do = dst_off.ctypes.data if hasattr(dst_off, "ctypes") else C.addressof(dst_off)
         self._check(self._L.czb_decode_batch_host_packed(self._h, src_base, so, dst_base, do, results_ptr, n, flags))
+
+    # ---- per-kernel timing ----
+    KERNEL_CLASSES = ["scan", "fill", "huff", "fse", "exec", "xxh64", "header_results", "other"]
+
+    def profile_enable(self, on=True):
+        self._check(self._L.czb_profile_enable(self._h, 1 if on else 0))
+
+    def profile_collect(self):
+        """Returns {class: (ms, launches)} accumulated since the last collect."""
+        ms = (C.c_double * 8)()
+        n = (C.c_uint64 * 8)()
+        self._check(self._L.czb_profile_collect(self._h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.KERNEL_CLASSES) if n[i]}
 
     # ---- debug taps ----
     def debug_last_wave(self):

@@ -72,11 +72,41 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     delete ctx;
 }
 
 extern "C" const char* czb_last_error(const czb_context* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
 extern "C" uint64_t czb_kernel_launches(const czb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- per-kernel profiling ----------------------------------------------------------------------
+static size_t prof_event(czb_context* ctx, cudaStream_t st) {
+    if (ctx->ev_used == ctx->ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+    cudaEventRecord(ctx->ev_pool[ctx->ev_used], st);
+    return ctx->ev_used++;
+}
+struct ProfScope {
+    czb_context* ctx; cudaStream_t st; int cls; size_t e0 = 0;
+    ProfScope(czb_context* c, cudaStream_t s, int k) : ctx(c), st(s), cls(k) { if (ctx->profiling) e0 = prof_event(ctx, st); }
+    ~ProfScope() { if (ctx->profiling) { size_t e1 = prof_event(ctx, st); ctx->prof.push_back({cls, e0, e1}); } }
+};
+extern "C" int czb_profile_enable(czb_context* ctx, int on) {
+    if (!ctx) return CZS_BAD_ARGUMENT;
+    ctx->profiling = on != 0;
+    return CZS_OK;
+}
+extern "C" int czb_profile_collect(czb_context* ctx, double* ms, uint64_t* launches) {
+    if (!ctx || !ms || !launches) return CZS_BAD_ARGUMENT;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (const auto& r : ctx->prof) {
+        CZB_CUDA(ctx, cudaEventSynchronize(ctx->ev_pool[r.e1]));
+        float t = 0;
+        CZB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->ev_pool[r.e0], ctx->ev_pool[r.e1]));
+        if (r.cls >= 0 && r.cls < CZB_PROFILE_CLASSES) { ms[r.cls] += t; launches[r.cls] += 1; }
+    }
+    ctx->prof.clear(); ctx->ev_used = 0;
+    return CZS_OK;
+}
 
 static uint64_t wave_scratch_bytes(const WaveTotals& t) {
     return t.n_blocks * sizeof(BlockDesc) + t.lit_bytes + t.n_seq * sizeof(Seq) + (t.n_huf + t.n_fse) * 4;
@@ -104,7 +134,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         n_waves = (n + W - 1) / W;
         if (attempt == 0) {
             CZB_CUDA(ctx, cudaMemsetAsync(ctx->totals_d.p, 0, n_waves * sizeof(WaveTotals), stream));
-            launch_scan_frames(lc, descs, ctx->infos.p, n, W, ctx->totals_d.p);
+            { ProfScope ps(ctx, stream, 0); launch_scan_frames(lc, descs, ctx->infos.p, n, W, ctx->totals_d.p); }
         } else {
             launch_wave_totals(lc, ctx->infos.p, n, W, ctx->totals_d.p, n_waves);
         }
@@ -128,16 +158,16 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
     if ((rc = ensure(ctx, ctx->lit, mx.lit_bytes + 64))) return rc;
     if ((rc = ensure(ctx, ctx->seq, mx.n_seq + 1))) return rc;
 
-    launch_header_results(lc, ctx->infos.p, results, n);
+    { ProfScope ps(ctx, stream, 6); launch_header_results(lc, ctx->infos.p, results, n); }
     for (uint64_t w = 0; w < n_waves; w++) {
         const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
         const WaveTotals& t = ctx->totals_h[w];
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(WaveCounters), stream));
-        launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->huf_items.p, ctx->fse_items.p, ctx->counters.p);
-        launch_huff(lc, descs + first, ctx->blocks.p, ctx->huf_items.p, ctx->counters.p, (uint32_t)t.n_huf, ctx->lit.p);
-        launch_fse(lc, descs + first, ctx->blocks.p, ctx->fse_items.p, ctx->counters.p, (uint32_t)t.n_fse, ctx->seq.p);
-        launch_exec(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->lit.p, ctx->seq.p, results);
-        if (flags & CZB_FLAG_VERIFY_CHECKSUM) launch_xxh64(lc, descs, results, first, count);
+        { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->huf_items.p, ctx->fse_items.p, ctx->counters.p); }
+        { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks.p, ctx->huf_items.p, ctx->counters.p, (uint32_t)t.n_huf, ctx->lit.p); }
+        { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks.p, ctx->fse_items.p, ctx->counters.p, (uint32_t)t.n_fse, ctx->seq.p); }
+        { ProfScope ps(ctx, stream, 4); launch_exec(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->lit.p, ctx->seq.p, results); }
+        if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, stream, 5); launch_xxh64(lc, descs, results, first, count); }
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count;
     }
     CZB_CUDA(ctx, cudaGetLastError());

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "czb_internal.cuh"
 
@@ -40,6 +41,13 @@ struct czb_context {
     uint8_t* pin_a = nullptr; uint64_t pin_a_cap = 0;
     uint8_t* pin_b = nullptr; uint64_t pin_b_cap = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr, compute = nullptr;
+
+    // per-kernel profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct ProfRec { int cls; size_t e0, e1; };
+    std::vector<ProfRec> prof;
 
     // debug taps
     czb::WaveTotals last_wave{};

@@ -163,6 +163,14 @@ int czb_debug_copy_sequences(czb_context* ctx, uint32_t* out /* 3 u32 per seq: l
 /* Number of kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t czb_kernel_launches(const czb_context* ctx);
 
+/* Per-kernel device timing (CUDA events recorded on the launching stream around every kernel).
+ * Classes: 0 scan, 1 fill, 2 huff, 3 fse, 4 exec, 5 xxh64, 6 header-results.
+ * czb_profile_collect synchronises on the recorded events, adds their elapsed times (ms) and
+ * launch counts per class into the arrays (8 entries each) and clears the recording. */
+#define CZB_PROFILE_CLASSES 8
+int czb_profile_enable(czb_context* ctx, int on);
+int czb_profile_collect(czb_context* ctx, double* ms, uint64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif
