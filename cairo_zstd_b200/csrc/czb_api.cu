@@ -393,7 +393,13 @@ extern "C" int czb_debug_copy_sequences(czb_context* ctx, uint32_t* out, uint64_
     CZB_CUDA(ctx, cudaSetDevice(ctx->device));
     CZB_CUDA(ctx, cudaDeviceSynchronize());
     const uint64_t ns = std::min<uint64_t>(cap_seqs, ctx->last_wave.n_seq);
-    if (ns) CZB_CUDA(ctx, cudaMemcpy(out, ctx->seq.p, ns * sizeof(Seq), cudaMemcpyDeviceToHost));
+    std::vector<Seq> h(ns);
+    if (ns) CZB_CUDA(ctx, cudaMemcpy(h.data(), ctx->seq.p, ns * sizeof(Seq), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < ns; i++) {
+        out[3 * i] = seq_ll(h[i]); out[3 * i + 1] = seq_ml(h[i]);
+        const uint32_t f = seq_off29(h[i]);
+        out[3 * i + 2] = (f >> 28) ? (0xF0000000u | (f & 0x0FFFFFFFu)) : f;  // symbolic references keep the high nibble set
+    }
     return CZS_OK;
 }
 

@@ -7,37 +7,52 @@
 // the append-only RingBuffer (ring_buffer.cairo:6) is simply the caller's dst span.
 //
 // Mapping: sequences are taken 32 at a time (lane = sequence).  A warp prefix sum over
-// literal/match lengths gives every sequence its literal source and output offsets; then the
-// chunk's output span is produced output-centrically: lane l computes output byte base+l, base+32+l, ...
-// by locating the segment (literal run or match) that owns it.  A match byte whose source lies
-// inside the same chunk is chased back through earlier segments until it reaches a literal or
-// already-written output, so overlapping matches (decode_buffer.cairo:101-120) and matches on
-// fresh output need no ordering between lanes, and all dst stores are coalesced.
-// HBM traffic per frame: literals + 12 B/sequence in, decoded bytes out, plus match re-reads that
-// mostly hit L1/L2 (recent output).
+// literal/match lengths gives every sequence its literal source and output offsets (segment
+// boundaries go to shared memory).  The chunk's output span is then produced in tiles of up to
+// 1 KiB: each lane owns a CONTIGUOUS run of the tile (equal byte counts per lane, so the work is
+// balanced no matter how lengths are distributed), walks the segments that cover its run and
+// copies bytes from the literal buffer or from earlier output into a shared-memory tile; the
+// tile is flushed to dst with aligned 16-byte stores.  A match byte whose source lies inside the
+// tile being built (or an overlapping match, decode_buffer.cairo:101-120) takes a per-byte path
+// that chases the source back through earlier segments, so no ordering between lanes is needed.
+// HBM traffic per frame: literals + 8 B/sequence in, decoded bytes out; match sources are recent
+// output and mostly hit L1/L2.
 #include "czb_internal.cuh"
 
 namespace czb {
 
 constexpr int EXEC_WARPS = 4;
+constexpr uint32_t EXEC_TILE = 1024;
 
 struct ExecWarpSmem {
-    uint32_t bound[65];   // bound[2i] = first output byte of sequence i's literal run, [2i+1] = of its match, [64] = span
+    uint32_t bound[66];   // bound[2i] = first output byte of sequence i's literal run, [2i+1] = of its match, [64] = span
     uint32_t lit_src[32]; // literal source offset of sequence i
     uint32_t off[32];     // actual match offset of sequence i
+    __align__(16) uint8_t tile[EXEC_TILE + 32];
 };
 
+// dst[0..n) = src[0..n): 16-byte stores to aligned dst; src may have any alignment (aligned
+// 32-bit loads + funnel shifts).  Only aligned words containing at least one source byte are read.
 __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t n) {
     const unsigned lane = lane_id();
-    // 16-byte path when both sides share alignment
-    if (n >= 512 && ((reinterpret_cast<uintptr_t>(dst) ^ reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+    if (n >= 64) {
         const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
         if (lane < head) dst[lane] = src[lane];
         dst += head; src += head; n -= head;
         const uint32_t nv = n >> 4;
-        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const uint32_t sh = (uint32_t)(sa & 3) * 8;
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
         uint4* d4 = reinterpret_cast<uint4*>(dst);
-        for (uint32_t i = lane; i < nv; i += 32) d4[i] = s4[i];
+        for (uint32_t i = lane; i < nv; i += 32) {
+            const uint32_t* w = sw + 4 * i;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+            const uint32_t w4 = sh ? w[4] : 0u;
+            uint4 v;
+            v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+            v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+            d4[i] = v;
+        }
         dst += nv << 4; src += nv << 4; n &= 15;
     }
     for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
@@ -45,7 +60,7 @@ __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8
 
 __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n) {
     const unsigned lane = lane_id();
-    if (n >= 512) {
+    if (n >= 64) {
         const uint32_t head = (uint32_t)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
         if (lane < head) dst[lane] = byte;
         dst += head; n -= head;
@@ -57,6 +72,15 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
         dst += nv << 4; n &= 15;
     }
     for (uint32_t i = lane; i < n; i += 32) dst[i] = byte;
+}
+
+// Largest kk in [0,63] with bound[kk] <= q (empty segments share a bound with their successor,
+// so the segment found is the non-empty one that contains q).
+__device__ __forceinline__ uint32_t find_segment(const uint32_t* bound, uint32_t q) {
+    uint32_t kk = 0;
+#pragma unroll
+    for (int stp = 32; stp > 0; stp >>= 1) if (bound[kk + stp] <= q) kk += stp;
+    return kk;
 }
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
@@ -74,9 +98,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
     const uint64_t cap = fd.dst_cap < MAX_FRAME_OUT ? fd.dst_cap : MAX_FRAME_OUT;
+    const int32_t cap_status = fd.dst_cap < MAX_FRAME_OUT ? CZS_DST_TOO_SMALL : CZS_UNSUPPORTED;
 
     uint64_t out = 0;  // bytes appended so far == DecodeBuffer.len() == total_output_counter
-    uint32_t hist[3] = {1, 4, 8};
+    uint32_t h0 = 1, h1 = 4, h2 = 8;  // scratch.cairo:35
     int32_t status = CZS_OK;
     uint32_t n_done = 0;
     uint64_t bytes_read = fi.hdr_len;
@@ -87,11 +112,11 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
         const uint64_t out_before = out;
         if (d.type == BT_ERROR) { status = d.pre_status; break; }
         if (d.type == BT_RAW) {
-            if (out + d.size > cap) { status = fd.dst_cap < MAX_FRAME_OUT ? CZS_DST_TOO_SMALL : CZS_UNSUPPORTED; break; }
+            if (out + d.size > cap) { status = cap_status; break; }
             warp_copy(dst + out, src + d.src_off, d.size);
             out += d.size; bytes_read += 3ull + d.size;
         } else if (d.type == BT_RLE) {
-            if (out + d.size > cap) { status = fd.dst_cap < MAX_FRAME_OUT ? CZS_DST_TOO_SMALL : CZS_UNSUPPORTED; break; }
+            if (out + d.size > cap) { status = cap_status; break; }
             warp_fill(dst + out, src[d.src_off], d.size);
             out += d.size; bytes_read += 4;
         } else {
@@ -111,15 +136,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
                 const uint32_t i = s0 + lane;
                 const bool have = i < d.n_seq;
                 uint32_t ll = 0, ml = 0, off = 1;
-                if (have) { const Seq q = seqs[i]; ll = q.ll; ml = q.ml; off = q.off; if (sym_is(off)) off = sym_resolve(off, hist); }
-                // warp prefix sums: literal offsets and output offsets
+                if (have) { const Seq q = seqs[i]; ll = seq_ll(q); ml = seq_ml(q); off = off29_resolve(seq_off29(q), h0, h1, h2); }
+                // warp prefix sums: literal offsets and output offsets (u32 cannot wrap: 32 * (131071 + 131074) < 2^32)
                 uint32_t lsum = ll, osum = ll + ml;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, lsum, o), b = __shfl_up_sync(0xFFFFFFFFu, osum, o);
                     if ((int)lane >= o) { lsum += a; osum += b; }
                 }
-                // note: u32 sums cannot wrap: 32 * (131071 + 131074) < 2^32
                 const uint32_t my_lit = lit_pos + lsum - ll;      // literals_copy_counter before this sequence
                 const uint32_t my_out = osum - ll - ml;           // output offset of the literal run, relative to chunk base
                 const uint64_t before_match = out + my_out + ll;  // DecodeBuffer.len() when repeat() is called
@@ -129,7 +153,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
                     else if (off == 0) err = CZS_EXEC_ZERO_OFFSET;                                            // :47-49
                     else if (ml > 0 && off > before_match)                                                      // decode_buffer.cairo:65-93
                         err = (before_match <= fi.window) ? CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY : CZS_OFFSET_TOO_BIG;
-                    else if (before_match + ml > cap) err = fd.dst_cap < MAX_FRAME_OUT ? CZS_DST_TOO_SMALL : CZS_UNSUPPORTED;
+                    else if (before_match + ml > cap) err = cap_status;
                 }
                 const unsigned errm = __ballot_sync(0xFFFFFFFFu, err != CZS_OK);
                 if (errm) { status = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1); break; }
@@ -137,44 +161,85 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
                 const uint32_t lit_used = __shfl_sync(0xFFFFFFFFu, lsum, 31);
                 sm.bound[2 * lane] = my_out; sm.bound[2 * lane + 1] = my_out + ll;
                 sm.lit_src[lane] = my_lit; sm.off[lane] = off;
-                if (lane == 0) sm.bound[64] = span;
+                if (lane == 0) { sm.bound[64] = span; sm.bound[65] = 0xFFFFFFFFu; }
                 __syncwarp();
                 uint8_t* obase = dst + out;
-                for (uint32_t p0 = 0; p0 < span; p0 += 32) {
-                    const uint32_t p = p0 + lane;
-                    if (p < span) {
-                        uint32_t q = p;
-                        uint32_t byte;
-                        for (;;) {
-                            // largest kk in [0,63] with bound[kk] <= q (empty segments share a bound with their successor)
-                            uint32_t kk = 0;
-#pragma unroll
-                            for (int stp = 32; stp > 0; stp >>= 1) if (sm.bound[kk + stp] <= q) kk += stp;
-                            const uint32_t sq = kk >> 1, rel = q - sm.bound[kk];
-                            if ((kk & 1) == 0) { byte = lit_rle ? rle_byte : lits[sm.lit_src[sq] + rel]; break; }
-                            const uint32_t o = sm.off[sq];
-                            const uint32_t r = rel >= o ? rel % o : rel;  // overlapping match = periodic pattern
-                            const int64_t srcpos = (int64_t)sm.bound[kk] + r - (int64_t)o;  // relative to chunk base
-                            if (srcpos < 0) { byte = obase[srcpos]; break; }
-                            q = (uint32_t)srcpos;  // inside this chunk: chase to an earlier segment
+                for (uint32_t t0 = 0; t0 < span; t0 += EXEC_TILE) {
+                    const uint32_t t_end = span - t0 < EXEC_TILE ? span : t0 + EXEC_TILE;
+                    const uint32_t nbytes = t_end - t0;
+                    uint8_t* g = obase + t0;
+                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
+                    uint8_t* tile = sm.tile + a0 - t0;  // tile[p] for chunk-relative p in [t0, t_end)
+                    const uint32_t per = (nbytes + 31) >> 5;
+                    uint32_t p = t0 + lane * per;
+                    const uint32_t r1 = p + per < t_end ? p + per : t_end;
+                    if (p < r1) {
+                        uint32_t kk = find_segment(sm.bound, p);
+                        while (p < r1) {
+                            const uint32_t seg0 = sm.bound[kk], seg_end = sm.bound[kk + 1];
+                            const uint32_t e = seg_end < r1 ? seg_end : r1;
+                            const uint32_t sq = kk >> 1;
+                            const uint8_t* sp = nullptr;
+                            if ((kk & 1) == 0) {
+                                if (!lit_rle) sp = lits + sm.lit_src[sq] + (p - seg0);
+                            } else {
+                                const uint32_t o = sm.off[sq];
+                                // contiguous source that is already in dst (before this tile): plain copy
+                                if (e - seg0 <= o && (int)(e - o) <= (int)t0) sp = obase + ((int64_t)p - (int64_t)o);
+                            }
+                            if (sp) {
+                                for (uint32_t q = p; q < e; q++) tile[q] = *sp++;
+                            } else if ((kk & 1) == 0) {
+                                for (uint32_t q = p; q < e; q++) tile[q] = (uint8_t)rle_byte;
+                            } else {
+                                // per-byte path: overlapping match and/or source inside the tile being built
+                                for (uint32_t q = p; q < e; q++) {
+                                    uint32_t kq = kk, pos = q, byte;
+                                    for (;;) {
+                                        const uint32_t ks = kq >> 1, rel = pos - sm.bound[kq];
+                                        if ((kq & 1) == 0) { byte = lit_rle ? rle_byte : lits[sm.lit_src[ks] + rel]; break; }
+                                        const uint32_t o = sm.off[ks];
+                                        const uint32_t r = rel >= o ? rel % o : rel;  // overlapping match = periodic pattern
+                                        const int srcpos = (int)sm.bound[kq] + (int)r - (int)o;  // relative to chunk base
+                                        if (srcpos < (int)t0) { byte = obase[srcpos]; break; }   // already flushed (or before the chunk)
+                                        pos = (uint32_t)srcpos;
+                                        kq = find_segment(sm.bound, pos);  // strictly earlier segment: terminates
+                                    }
+                                    tile[q] = (uint8_t)byte;
+                                }
+                            }
+                            p = e;
+                            if (p < r1) { kk++; while (sm.bound[kk + 1] <= p) kk++; }
                         }
-                        obase[p] = (uint8_t)byte;
                     }
+                    __syncwarp();
+                    // flush the tile: aligned 16-byte stores (tile index and dst address agree modulo 16)
+                    {
+                        const uint32_t head = nbytes < ((16 - a0) & 15) ? nbytes : ((16 - a0) & 15);
+                        if (lane < head) g[lane] = sm.tile[a0 + lane];
+                        const uint32_t body = nbytes - head;
+                        const uint32_t nv = body >> 4;
+                        const uint4* t4 = reinterpret_cast<const uint4*>(sm.tile + a0 + head);
+                        uint4* g4 = reinterpret_cast<uint4*>(g + head);
+                        for (uint32_t v = lane; v < nv; v += 32) g4[v] = t4[v];
+                        const uint32_t tail = body & 15;
+                        if (lane < tail) g[head + (nv << 4) + lane] = sm.tile[a0 + head + (nv << 4) + lane];
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 out += span; lit_pos += lit_used;
             }
             if (status != CZS_OK) break;
             if (d.n_seq) {  // history after this block (resolved against the history it started from)
-                uint32_t nh[3];
-#pragma unroll
-                for (int j = 0; j < 3; j++) nh[j] = sym_is(d.hist_out[j]) ? sym_resolve(d.hist_out[j], hist) : d.hist_out[j];
-                hist[0] = nh[0]; hist[1] = nh[1]; hist[2] = nh[2];
+                const uint32_t n0 = sym_is(d.hist_out[0]) ? sym_resolve(d.hist_out[0], h0, h1, h2) : d.hist_out[0];
+                const uint32_t n1 = sym_is(d.hist_out[1]) ? sym_resolve(d.hist_out[1], h0, h1, h2) : d.hist_out[1];
+                const uint32_t n2 = sym_is(d.hist_out[2]) ? sym_resolve(d.hist_out[2], h0, h1, h2) : d.hist_out[2];
+                h0 = n0; h1 = n1; h2 = n2;
             }
             // rest literals (:72-78), or all literals when there are no sequences (block_decoder.cairo:229-232)
             const uint32_t rest = n_lit - lit_pos;
             if (rest) {
-                if (out + rest > cap) { status = fd.dst_cap < MAX_FRAME_OUT ? CZS_DST_TOO_SMALL : CZS_UNSUPPORTED; break; }
+                if (out + rest > cap) { status = cap_status; break; }
                 if (lit_rle) warp_fill(dst + out, (uint8_t)rle_byte, rest);
                 else warp_copy(dst + out, lits + lit_pos, rest);
                 out += rest;
@@ -189,7 +254,6 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
         }
         __syncwarp();
     }
-    // A frame whose last block is followed by a missing checksum trailer: the pseudo block reports the trap.
     if (lane == 0) {
         czb_frame_result r;
         r.status = status;

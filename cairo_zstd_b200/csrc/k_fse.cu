@@ -8,18 +8,18 @@
 // chain over the same sequences.
 //
 // Mapping: the interleaved LL/OF/ML state machine is one dependency chain per block and cannot be
-// split, so parallelism comes from blocks: a CTA owns 32 blocks, all 8 warps build the 96 tables
+// split, so parallelism comes from blocks: a CTA owns 27 blocks, its 4 warps build the 81 tables
 // cooperatively, then warp 0 decodes with lane = block.  Throughput is bounded by
 // (blocks resident per SM) / (chain latency per sequence); 16-bit table entries (czb_fse_build.cuh)
-// keep a block's three tables at <= 2.5 KiB so 64 blocks fit per SM.  HBM traffic: the bitstream in
-// (a few bytes per sequence) and 12 B per sequence out to scratch.
+// keep a block's three tables at <= 2.5 KiB so 81 blocks fit per SM (three CTAs).  HBM traffic: the
+// bitstream in (a few bytes per sequence) and one packed 8-byte record per sequence out to scratch.
 #include "czb_fse_build.cuh"
 #include "czb_internal.cuh"
 
 namespace czb {
 
-constexpr int FSE_WARPS = 8;
-constexpr int FSE_SLOTS = 32;
+constexpr int FSE_WARPS = 4;
+constexpr int FSE_SLOTS = 27;  // 27 * 2560 B of tables + scratch = ~75 KB -> three CTAs (81 decode lanes) per SM
 constexpr int FSE_SLOT_ENTRIES = 512 + 512 + 256;  // LL (log<=9), ML (log<=9), OF (log<=8)
 constexpr int FSE_LL_OFS = 0, FSE_ML_OFS = 512, FSE_OF_OFS = 1024;
 
@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32) k_fse(const czb_frame_desc* __
     if (warp != 0) return;
 
     // ---- phase 2: lane = block ----
+    if (lane >= FSE_SLOTS) return;
     const FseSlot& sl = sm.slot[lane];
     if (sl.blk == NONE32) return;
     int32_t st = sl.status;
@@ -197,55 +198,63 @@ __global__ void __launch_bounds__(FSE_WARPS * 32) k_fse(const czb_frame_desc* __
         else if (sl.log[0] < 0 || sl.log[1] < 0 || sl.log[2] < 0) st = CZS_FSE_TABLE_IS_UNINITIALIZED;  // fse_decoder.cairo:82-84
         else {
             const uint32_t logLL = (uint32_t)sl.log[0], logOF = (uint32_t)sl.log[1], logML = (uint32_t)sl.log[2];
+            const uint32_t mLL = (1u << logLL) - 1u, mOF = (1u << logOF) - 1u, mML = (1u << logML) - 1u;
             const uint16_t* tLL = sm.entries + sl.tbl[0];
             const uint16_t* tOF = sm.entries + sl.tbl[1];
             const uint16_t* tML = sm.entries + sl.tbl[2];
-            // init order LL, OF, ML (:207-218)
+            // init order LL, OF, ML (:207-218): at most 26 bits, the reader holds more than 32
             uint32_t eLL = tLL[br.get((int)logLL)];
             uint32_t eOF = tOF[br.get((int)logOF)];
             uint32_t eML = tML[br.get((int)logML)];
             const uint32_t n_seq = sl.n_seq;
             Seq* out = sl.out;
             for (uint32_t i = 0; i < n_seq; i++) {  // hot loop :223-286
-                if (br.avail <= 32) br.refill();
+                br.topup_if_low();  // avail > 32 from here
                 const uint32_t llc = fse_entry_sym(eLL), mlc = fse_entry_sym(eML), ofc = fse_entry_sym(eOF);
-                if (ofc >= 32) { st = CZS_SEQ_UNSUPPORTED_OFFSET; break; }       // :235-237
-                if (mlc > 52 || llc > 35) { st = CZS_SEQ_GET_BITS_ERROR; break; }  // (0,255) -> TooManyBits
+                if ((ofc >= 32) | (mlc > 52) | (llc > 35)) {  // :235-237; (0,255) -> TooManyBits
+                    st = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
+                    break;
+                }
                 const uint32_t lle = sm.ll_code[llc], mle = sm.ml_code[mlc];
-                const int llb = (int)(lle >> 20), mlb = (int)(mle >> 20);
-                uint32_t ofv, mlv, llv;
-                if ((int)ofc + mlb + llb <= br.avail) {  // read order OF, ML, LL (:239)
-                    ofv = br.get((int)ofc); mlv = br.get(mlb); llv = br.get(llb);
-                } else {
+                const uint32_t llb = lle >> 20, mlb = mle >> 20;
+                const bool more = i + 1 < n_seq;  // states are not updated after the last sequence (:258)
+                const uint32_t nbLL = more ? fse_entry_nbits(eLL, logLL) : 0u, nbML = more ? fse_entry_nbits(eML, logML) : 0u,
+                               nbOF = more ? fse_entry_nbits(eOF, logOF) : 0u;
+                const uint32_t total = ofc + mlb + llb + nbLL + nbML + nbOF;
+                uint32_t ofv, mlv, llv, aLL, aML, aOF;
+                if (total <= 32) {
+                    // every field comes out of the top 32 bits: read order OF, ML, LL (:239) then LL, ML, OF (:258-276)
+                    const uint32_t w = (uint32_t)(br.buf >> 32);
+                    uint32_t pos = 32 - ofc;
+                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(ofv) : "r"(w), "r"(pos), "r"(ofc)); pos -= mlb;
+                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(mlv) : "r"(w), "r"(pos), "r"(mlb)); pos -= llb;
+                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(llv) : "r"(w), "r"(pos), "r"(llb)); pos -= nbLL;
+                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(aLL) : "r"(w), "r"(pos), "r"(nbLL)); pos -= nbML;
+                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(aML) : "r"(w), "r"(pos), "r"(nbML)); pos -= nbOF;
+                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(aOF) : "r"(w), "r"(pos), "r"(nbOF));
+                    br.skip((int)total);
+                } else {  // rare: long offsets with long extra bits
                     ofv = br.get((int)ofc);
-                    if (br.avail <= 32) br.refill();
-                    mlv = br.get(mlb); llv = br.get(llb);
+                    mlv = br.get_safe((int)mlb); llv = br.get_safe((int)llb);
+                    aLL = br.get_safe((int)nbLL); aML = br.get_safe((int)nbML); aOF = br.get_safe((int)nbOF);
                 }
                 const uint32_t v = (1u << ofc) + ofv;  // :243
                 const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
-                // do_offset_history (sequence_execution.cairo:85-129)
-                uint32_t act;
-                if (ll > 0) {
-                    if (v == 1) act = h0;
-                    else if (v == 2) { act = h1; h1 = h0; h0 = act; }
-                    else if (v == 3) { act = h2; h2 = h1; h1 = h0; h0 = act; }
-                    else { act = v - 3; if (act >= SYM_BASE) act = REAL_OFF_CLAMP; h2 = h1; h1 = h0; h0 = act; }
-                } else {
-                    if (v == 1) { act = h1; h1 = h0; h0 = act; }
-                    else if (v == 2) { act = h2; h2 = h1; h1 = h0; h0 = act; }
-                    else if (v == 3) { act = h0 - 1; h2 = h1; h1 = h0; h0 = act; }
-                    else { act = v - 3; if (act >= SYM_BASE) act = REAL_OFF_CLAMP; h2 = h1; h1 = h0; h0 = act; }
-                }
-                out[i].ll = ll; out[i].ml = ml; out[i].off = act;
-                if (i + 1 < n_seq) {  // update order LL, ML, OF (:258-276)
-                    if (br.avail <= 32) br.refill();
-                    const uint32_t nbLL = fse_entry_nbits(eLL, logLL), nbML = fse_entry_nbits(eML, logML), nbOF = fse_entry_nbits(eOF, logOF);
-                    const uint32_t sLL = fse_entry_base(eLL, nbLL, logLL) + br.get((int)nbLL);
-                    const uint32_t sML = fse_entry_base(eML, nbML, logML) + br.get((int)nbML);
-                    const uint32_t sOF = fse_entry_base(eOF, nbOF, logOF) + br.get((int)nbOF);
-                    eLL = tLL[sLL & ((1u << logLL) - 1u)];
-                    eML = tML[sML & ((1u << logML) - 1u)];
-                    eOF = tOF[sOF & ((1u << logOF) - 1u)];
+                // do_offset_history (sequence_execution.cairo:85-129), branch-free
+                const uint32_t idx = v - (ll ? 1u : 0u);      // 0,1,2: history slot; 3: h0 - 1 (only when ll == 0)
+                const bool rep = v <= 3;
+                const uint32_t cand = idx == 0 ? h0 : (idx == 1 ? h1 : (idx == 2 ? h2 : h0 - 1u));
+                uint32_t nz = v - 3u; if (nz >= SYM_BASE) nz = REAL_OFF_CLAMP;
+                const uint32_t act = rep ? cand : nz;
+                const bool keep1 = rep & (idx == 0), keep2 = rep & (idx <= 1);
+                h2 = keep2 ? h2 : h1;
+                h1 = keep1 ? h1 : h0;
+                h0 = act;
+                out[i] = (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35);
+                if (more) {
+                    eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
+                    eML = tML[(fse_entry_base(eML, nbML, logML) + aML) & mML];
+                    eOF = tOF[(fse_entry_base(eOF, nbOF, logOF) + aOF) & mOF];
                 }
                 if (br.rem < 0) {  // :281-283; the no-RLE variant traps on the unwrap at :279 instead
                     st = sl.any_rle ? CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES : CZS_PANIC_INTERNAL;
