@@ -7,14 +7,15 @@
 // the append-only RingBuffer (ring_buffer.cairo:6) is simply the caller's dst span.
 //
 // Mapping: sequences are taken 32 at a time (lane = sequence).  A warp prefix sum over
-// literal/match lengths gives every sequence its literal source and output offsets (segment
-// boundaries go to shared memory).  The chunk's output span is then produced in tiles of up to
-// 1 KiB: each lane owns a CONTIGUOUS run of the tile (equal byte counts per lane, so the work is
-// balanced no matter how lengths are distributed), walks the segments that cover its run and
-// copies bytes from the literal buffer or from earlier output into a shared-memory tile; the
-// tile is flushed to dst with aligned 16-byte stores.  A match byte whose source lies inside the
-// tile being built (or an overlapping match, decode_buffer.cairo:101-120) takes a per-byte path
-// that chases the source back through earlier segments, so no ordering between lanes is needed.
+// literal/match lengths gives every sequence its literal source and output offsets; each of the
+// 64 segments (literal run / match per sequence) publishes its start and a source delta in shared
+// memory.  The chunk's output span is then produced OUTPUT-CENTRICALLY in rows of 128 bytes that are
+// 4-byte aligned in dst: lane l owns the aligned word at row + 4l.  Segment ownership of every row
+// byte comes from one warp max-scan over "segment id at its start byte" marks; each byte is then a
+// single gather (literal buffer or earlier output at p + delta) and the word is stored with one
+// coalesced 32-bit store.  Control flow is uniform across lanes.  Only bytes whose source lies
+// inside the row being built, overlapping matches (decode_buffer.cairo:101-120) and RLE literals
+// take a per-byte path that chases the source back through the row's segment map.
 // HBM traffic per frame: literals + 8 B/sequence in, decoded bytes out; match sources are recent
 // output and mostly hit L1/L2.
 #include "czb_internal.cuh"
@@ -22,14 +23,16 @@
 namespace czb {
 
 constexpr int EXEC_WARPS = 4;
-constexpr uint32_t EXEC_TILE = 1024;
+constexpr uint32_t EXEC_ROW = 128;
 
 struct ExecWarpSmem {
-    uint32_t bound[66];   // bound[2i] = first output byte of sequence i's literal run, [2i+1] = of its match, [64] = span
-    uint32_t lit_src[32]; // literal source offset of sequence i
-    uint32_t off[32];     // actual match offset of sequence i
-    __align__(16) uint8_t tile[EXEC_TILE + 32];
+    uint32_t bound[66];      // bound[2i] = first output byte of sequence i's literal run, [2i+1] = of its match, [64] = span
+    uint32_t segdelta[64];   // per segment: bit 31 = per-byte path, bit 30 = literal, low 30 bits = signed source delta
+    __align__(4) uint8_t rowmap[EXEC_ROW];  // (segment id + 1) at each non-empty segment's start byte inside the row
+    __align__(4) uint8_t krow[EXEC_ROW];    // (segment id + 1) owning each row byte
 };
+
+__device__ __forceinline__ int seg_sdelta(uint32_t d) { return ((int)(d << 2)) >> 2; }
 
 // dst[0..n) = src[0..n): 16-byte stores to aligned dst; src may have any alignment (aligned
 // 32-bit loads + funnel shifts).  Only aligned words containing at least one source byte are read.
@@ -72,15 +75,6 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
         dst += nv << 4; n &= 15;
     }
     for (uint32_t i = lane; i < n; i += 32) dst[i] = byte;
-}
-
-// Largest kk in [0,63] with bound[kk] <= q (empty segments share a bound with their successor,
-// so the segment found is the non-empty one that contains q).
-__device__ __forceinline__ uint32_t find_segment(const uint32_t* bound, uint32_t q) {
-    uint32_t kk = 0;
-#pragma unroll
-    for (int stp = 32; stp > 0; stp >>= 1) if (bound[kk + stp] <= q) kk += stp;
-    return kk;
 }
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
@@ -159,71 +153,74 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
                 if (errm) { status = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1); break; }
                 const uint32_t span = __shfl_sync(0xFFFFFFFFu, osum, 31);
                 const uint32_t lit_used = __shfl_sync(0xFFFFFFFFu, lsum, 31);
-                sm.bound[2 * lane] = my_out; sm.bound[2 * lane + 1] = my_out + ll;
-                sm.lit_src[lane] = my_lit; sm.off[lane] = off;
-                if (lane == 0) { sm.bound[64] = span; sm.bound[65] = 0xFFFFFFFFu; }
-                __syncwarp();
+                // publish the 64 segments of this chunk
+                const uint32_t segA = my_out, segM = my_out + ll;
+                sm.bound[2 * lane] = segA; sm.bound[2 * lane + 1] = segM;
+                sm.segdelta[2 * lane] = ((my_lit - segA) & 0x3FFFFFFFu) | 0x40000000u | (lit_rle ? 0x80000000u : 0u);
+                sm.segdelta[2 * lane + 1] = ((0u - off) & 0x3FFFFFFFu) | ((off < ml || off < EXEC_ROW) ? 0x80000000u : 0u);
+                if (lane == 0) sm.bound[64] = span;
                 uint8_t* obase = dst + out;
-                for (uint32_t t0 = 0; t0 < span; t0 += EXEC_TILE) {
-                    const uint32_t t_end = span - t0 < EXEC_TILE ? span : t0 + EXEC_TILE;
-                    const uint32_t nbytes = t_end - t0;
-                    uint8_t* g = obase + t0;
-                    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
-                    uint8_t* tile = sm.tile + a0 - t0;  // tile[p] for chunk-relative p in [t0, t_end)
-                    const uint32_t per = (nbytes + 31) >> 5;
-                    uint32_t p = t0 + lane * per;
-                    const uint32_t r1 = p + per < t_end ? p + per : t_end;
-                    if (p < r1) {
-                        uint32_t kk = find_segment(sm.bound, p);
-                        while (p < r1) {
-                            const uint32_t seg0 = sm.bound[kk], seg_end = sm.bound[kk + 1];
-                            const uint32_t e = seg_end < r1 ? seg_end : r1;
-                            const uint32_t sq = kk >> 1;
-                            const uint8_t* sp = nullptr;
-                            if ((kk & 1) == 0) {
-                                if (!lit_rle) sp = lits + sm.lit_src[sq] + (p - seg0);
-                            } else {
-                                const uint32_t o = sm.off[sq];
-                                // contiguous source that is already in dst (before this tile): plain copy
-                                if (e - seg0 <= o && (int)(e - o) <= (int)t0) sp = obase + ((int64_t)p - (int64_t)o);
+                const int a = (int)(reinterpret_cast<uintptr_t>(obase) & 3);
+                uint32_t carry = 0;
+                for (int r = -a; r < (int)span; r += (int)EXEC_ROW) {
+                    // ---- which segment owns each byte of the row ----
+                    *reinterpret_cast<uint32_t*>(&sm.rowmap[4 * lane]) = 0u;
+                    __syncwarp();
+                    if (ll && (uint32_t)((int)segA - r) < EXEC_ROW) sm.rowmap[(int)segA - r] = (uint8_t)(2 * lane + 1);
+                    if (ml && (uint32_t)((int)segM - r) < EXEC_ROW) sm.rowmap[(int)segM - r] = (uint8_t)(2 * lane + 2);
+                    __syncwarp();
+                    uint32_t x = *reinterpret_cast<const uint32_t*>(&sm.rowmap[4 * lane]);
+                    x = __vmaxu4(x, x << 8);
+                    x = __vmaxu4(x, x << 16);  // running maximum inside the word (ids grow with position)
+                    uint32_t tot = x >> 24;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, tot, o); if ((int)lane >= o) tot = max(tot, t); }
+                    uint32_t excl = __shfl_up_sync(0xFFFFFFFFu, tot, 1);
+                    if (lane == 0) excl = 0;
+                    x = __vmaxu4(x, max(excl, carry) * 0x01010101u);
+                    carry = __shfl_sync(0xFFFFFFFFu, x >> 24, 31);
+                    *reinterpret_cast<uint32_t*>(&sm.krow[4 * lane]) = x;
+                    __syncwarp();
+                    // ---- gather the four bytes of this lane's word ----
+                    const int p0 = r + 4 * (int)lane;
+                    uint32_t word = 0, slow_mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int p = p0 + j;
+                        const bool valid = (uint32_t)p < span;
+                        const uint32_t kj = (x >> (8 * j)) & 0xFFu;
+                        const uint32_t d = sm.segdelta[kj ? kj - 1 : 0];
+                        const uint8_t* base = (d & 0x40000000u) ? lits : obase;
+                        const bool fast = valid && !(d >> 31);
+                        uint32_t b = 0;
+                        if (fast) b = base[(int64_t)p + seg_sdelta(d)];
+                        word |= b << (8 * j);
+                        if (valid && (d >> 31)) slow_mask |= 1u << j;
+                    }
+                    if (__any_sync(0xFFFFFFFFu, slow_mask != 0)) {
+                        for (int j = 0; j < 4; j++) {
+                            if (!((slow_mask >> j) & 1)) continue;
+                            int p = p0 + j;
+                            uint32_t kq = ((x >> (8 * j)) & 0xFFu) - 1u, byte;
+                            for (;;) {
+                                const uint32_t d = sm.segdelta[kq];
+                                const int sd = seg_sdelta(d);
+                                if (d & 0x40000000u) { byte = lit_rle ? rle_byte : lits[p + sd]; break; }
+                                const uint32_t o = (uint32_t)(-sd), seg0 = sm.bound[kq];
+                                uint32_t rel = (uint32_t)p - seg0;
+                                if (rel >= o) rel %= o;  // overlapping match = periodic pattern (decode_buffer.cairo:101-120)
+                                const int q = (int)seg0 + (int)rel - (int)o;  // chunk-relative source position
+                                if (q < r || q < 0) { byte = obase[q]; break; }  // earlier rows / chunks are already in dst
+                                kq = (uint32_t)sm.krow[q - r] - 1u;            // same row, strictly earlier byte: chase
+                                p = q;
                             }
-                            if (sp) {
-                                for (uint32_t q = p; q < e; q++) tile[q] = *sp++;
-                            } else if ((kk & 1) == 0) {
-                                for (uint32_t q = p; q < e; q++) tile[q] = (uint8_t)rle_byte;
-                            } else {
-                                // per-byte path: overlapping match and/or source inside the tile being built
-                                for (uint32_t q = p; q < e; q++) {
-                                    uint32_t kq = kk, pos = q, byte;
-                                    for (;;) {
-                                        const uint32_t ks = kq >> 1, rel = pos - sm.bound[kq];
-                                        if ((kq & 1) == 0) { byte = lit_rle ? rle_byte : lits[sm.lit_src[ks] + rel]; break; }
-                                        const uint32_t o = sm.off[ks];
-                                        const uint32_t r = rel >= o ? rel % o : rel;  // overlapping match = periodic pattern
-                                        const int srcpos = (int)sm.bound[kq] + (int)r - (int)o;  // relative to chunk base
-                                        if (srcpos < (int)t0) { byte = obase[srcpos]; break; }   // already flushed (or before the chunk)
-                                        pos = (uint32_t)srcpos;
-                                        kq = find_segment(sm.bound, pos);  // strictly earlier segment: terminates
-                                    }
-                                    tile[q] = (uint8_t)byte;
-                                }
-                            }
-                            p = e;
-                            if (p < r1) { kk++; while (sm.bound[kk + 1] <= p) kk++; }
+                            word |= byte << (8 * j);
                         }
                     }
-                    __syncwarp();
-                    // flush the tile: aligned 16-byte stores (tile index and dst address agree modulo 16)
-                    {
-                        const uint32_t head = nbytes < ((16 - a0) & 15) ? nbytes : ((16 - a0) & 15);
-                        if (lane < head) g[lane] = sm.tile[a0 + lane];
-                        const uint32_t body = nbytes - head;
-                        const uint32_t nv = body >> 4;
-                        const uint4* t4 = reinterpret_cast<const uint4*>(sm.tile + a0 + head);
-                        uint4* g4 = reinterpret_cast<uint4*>(g + head);
-                        for (uint32_t v = lane; v < nv; v += 32) g4[v] = t4[v];
-                        const uint32_t tail = body & 15;
-                        if (lane < tail) g[head + (nv << 4) + lane] = sm.tile[a0 + head + (nv << 4) + lane];
+                    if (p0 >= 0 && (uint32_t)(p0 + 3) < span) *reinterpret_cast<uint32_t*>(obase + p0) = word;
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) if ((uint32_t)(p0 + j) < span) obase[p0 + j] = (uint8_t)(word >> (8 * j));
                     }
                     __syncwarp();
                 }

@@ -13,6 +13,8 @@
 // (blocks resident per SM) / (chain latency per sequence); 16-bit table entries (czb_fse_build.cuh)
 // keep a block's three tables at <= 2.5 KiB so 81 blocks fit per SM (three CTAs).  HBM traffic: the
 // bitstream in (a few bytes per sequence) and one packed 8-byte record per sequence out to scratch.
+#include <type_traits>
+
 #include "czb_fse_build.cuh"
 #include "czb_internal.cuh"
 
@@ -45,8 +47,8 @@ struct FseSmem {
     uint16_t entries[FSE_SLOTS * FSE_SLOT_ENTRIES + 64 + 32 + 64];  // per-slot tables, then predefined LL, OF, ML
     FseSlot slot[FSE_SLOTS];
     FseWarpTmp tmp[FSE_WARPS];
-    uint32_t ll_code[36];  // base | bits << 20 (lookup_ll_code :299-345)
-    uint32_t ml_code[53];  // (lookup_ml_code :347-395)
+    uint32_t ll_code[64];  // base | bits << 20 (lookup_ll_code :299-345); bit 31 = code beyond the table -> (0,255)
+    uint32_t ml_code[64];  // (lookup_ml_code :347-395)
 };
 constexpr int FSE_PREDEF_LL = FSE_SLOTS * FSE_SLOT_ENTRIES, FSE_PREDEF_OF = FSE_PREDEF_LL + 64, FSE_PREDEF_ML = FSE_PREDEF_OF + 32;
 
@@ -89,8 +91,8 @@ __global__ void __launch_bounds__(FSE_WARPS * 32) k_fse(const czb_frame_desc* __
         fse_build_table_warp(tmp.probs, n, warp == 1 ? 5 : 6,
                              sm.entries + (warp == 0 ? FSE_PREDEF_LL : (warp == 1 ? FSE_PREDEF_OF : FSE_PREDEF_ML)), tmp.rank_sym);
     } else if (warp == 3) {
-        for (int i = lane; i < 36; i += 32) sm.ll_code[i] = kLLBase[i] | ((uint32_t)kLLBits[i] << 20);
-        for (int i = lane; i < 53; i += 32) sm.ml_code[i] = kMLBase[i] | ((uint32_t)kMLBits[i] << 20);
+        for (int i = lane; i < 64; i += 32) sm.ll_code[i] = i < 36 ? (kLLBase[i] | ((uint32_t)kLLBits[i] << 20)) : 0x80000000u;
+        for (int i = lane; i < 64; i += 32) sm.ml_code[i] = i < 53 ? (kMLBase[i] | ((uint32_t)kMLBits[i] << 20)) : 0x80000000u;
     }
     __syncwarp();
 
@@ -208,59 +210,71 @@ __global__ void __launch_bounds__(FSE_WARPS * 32) k_fse(const czb_frame_desc* __
             uint32_t eML = tML[br.get((int)logML)];
             const uint32_t n_seq = sl.n_seq;
             Seq* out = sl.out;
-            for (uint32_t i = 0; i < n_seq; i++) {  // hot loop :223-286
+            const bool any_rle = sl.any_rle;
+            // One sequence (:223-286).  MORE = false is the last sequence: states are not updated (:258).
+            auto step = [&](uint32_t i, auto more_tag) -> bool {
+                constexpr bool MORE = decltype(more_tag)::value;
                 br.topup_if_low();  // avail > 32 from here
                 const uint32_t llc = fse_entry_sym(eLL), mlc = fse_entry_sym(eML), ofc = fse_entry_sym(eOF);
-                if ((ofc >= 32) | (mlc > 52) | (llc > 35)) {  // :235-237; (0,255) -> TooManyBits
-                    st = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
-                    break;
-                }
                 const uint32_t lle = sm.ll_code[llc], mle = sm.ml_code[mlc];
+                if ((ofc >> 5) | ((lle | mle) >> 31)) {  // :235-237; codes beyond the tables give (0,255) -> TooManyBits
+                    st = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
+                    return false;
+                }
                 const uint32_t llb = lle >> 20, mlb = mle >> 20;
-                const bool more = i + 1 < n_seq;  // states are not updated after the last sequence (:258)
-                const uint32_t nbLL = more ? fse_entry_nbits(eLL, logLL) : 0u, nbML = more ? fse_entry_nbits(eML, logML) : 0u,
-                               nbOF = more ? fse_entry_nbits(eOF, logOF) : 0u;
+                uint32_t nbLL = 0, nbML = 0, nbOF = 0;
+                if (MORE) { nbLL = fse_entry_nbits(eLL, logLL); nbML = fse_entry_nbits(eML, logML); nbOF = fse_entry_nbits(eOF, logOF); }
                 const uint32_t total = ofc + mlb + llb + nbLL + nbML + nbOF;
-                uint32_t ofv, mlv, llv, aLL, aML, aOF;
+                uint32_t ofv, mlv, llv, aLL = 0, aML = 0, aOF = 0;
                 if (total <= 32) {
-                    // every field comes out of the top 32 bits: read order OF, ML, LL (:239) then LL, ML, OF (:258-276)
-                    const uint32_t w = (uint32_t)(br.buf >> 32);
-                    uint32_t pos = 32 - ofc;
-                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(ofv) : "r"(w), "r"(pos), "r"(ofc)); pos -= mlb;
-                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(mlv) : "r"(w), "r"(pos), "r"(mlb)); pos -= llb;
-                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(llv) : "r"(w), "r"(pos), "r"(llb)); pos -= nbLL;
-                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(aLL) : "r"(w), "r"(pos), "r"(nbLL)); pos -= nbML;
-                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(aML) : "r"(w), "r"(pos), "r"(nbML)); pos -= nbOF;
-                    asm("bfe.u32 %0, %1, %2, %3;" : "=r"(aOF) : "r"(w), "r"(pos), "r"(nbOF));
+                    // every field comes out of the top 32 bits: read order OF, ML, LL (:239) then LL, ML, OF (:258-276).
+                    // PTX shl/shr clamp the shift amount, so zero-width fields read as 0.
+                    uint32_t x = (uint32_t)(br.buf >> 32);
+                    auto take = [&x](uint32_t n) -> uint32_t {
+                        uint32_t v, sh = 32u - n;
+                        asm("shr.b32 %0, %1, %2;" : "=r"(v) : "r"(x), "r"(sh));
+                        asm("shl.b32 %0, %1, %2;" : "=r"(x) : "r"(x), "r"(n));
+                        return v;
+                    };
+                    ofv = take(ofc); mlv = take(mlb); llv = take(llb);
+                    if (MORE) { aLL = take(nbLL); aML = take(nbML); aOF = take(nbOF); }
                     br.skip((int)total);
                 } else {  // rare: long offsets with long extra bits
                     ofv = br.get((int)ofc);
                     mlv = br.get_safe((int)mlb); llv = br.get_safe((int)llb);
-                    aLL = br.get_safe((int)nbLL); aML = br.get_safe((int)nbML); aOF = br.get_safe((int)nbOF);
+                    if (MORE) { aLL = br.get_safe((int)nbLL); aML = br.get_safe((int)nbML); aOF = br.get_safe((int)nbOF); }
                 }
                 const uint32_t v = (1u << ofc) + ofv;  // :243
                 const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
-                // do_offset_history (sequence_execution.cairo:85-129), branch-free
-                const uint32_t idx = v - (ll ? 1u : 0u);      // 0,1,2: history slot; 3: h0 - 1 (only when ll == 0)
+                // do_offset_history (sequence_execution.cairo:85-129) with selects only:
+                // idx 0,1,2 = history slot, 3 = h0 - 1 (reachable only when ll == 0)
+                const uint32_t idx = v - (ll != 0);
                 const bool rep = v <= 3;
-                const uint32_t cand = idx == 0 ? h0 : (idx == 1 ? h1 : (idx == 2 ? h2 : h0 - 1u));
-                uint32_t nz = v - 3u; if (nz >= SYM_BASE) nz = REAL_OFF_CLAMP;
+                uint32_t cand = h0 - 1u;
+                cand = idx == 2 ? h2 : cand;
+                cand = idx == 1 ? h1 : cand;
+                cand = idx == 0 ? h0 : cand;
+                const uint32_t nz = min(v - 3u, REAL_OFF_CLAMP);
                 const uint32_t act = rep ? cand : nz;
-                const bool keep1 = rep & (idx == 0), keep2 = rep & (idx <= 1);
-                h2 = keep2 ? h2 : h1;
-                h1 = keep1 ? h1 : h0;
+                h2 = (rep & (idx <= 1)) ? h2 : h1;
+                h1 = (rep & (idx == 0)) ? h1 : h0;
                 h0 = act;
                 out[i] = (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35);
-                if (more) {
+                if (MORE) {
                     eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
                     eML = tML[(fse_entry_base(eML, nbML, logML) + aML) & mML];
                     eOF = tOF[(fse_entry_base(eOF, nbOF, logOF) + aOF) & mOF];
                 }
                 if (br.rem < 0) {  // :281-283; the no-RLE variant traps on the unwrap at :279 instead
-                    st = sl.any_rle ? CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES : CZS_PANIC_INTERNAL;
-                    break;
+                    st = any_rle ? CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES : CZS_PANIC_INTERNAL;
+                    return false;
                 }
-            }
+                return true;
+            };
+            bool ok = true;
+            uint32_t i = 0;
+            for (; ok && i + 1 < n_seq; i++) ok = step(i, std::true_type{});
+            if (ok) step(i, std::false_type{});
             if (st == CZS_OK && br.rem > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
         }
     }
