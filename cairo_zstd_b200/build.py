@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CZB_NVCC_FLAGS", "").split() + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     fail = False

@@ -53,7 +53,12 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     if (cudaMallocHost(reinterpret_cast<void**>(&ctx->totals_h), sizeof(WaveTotals) * kMaxWaves) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
     if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+        cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->exec_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    for (int s = 0; s < 2; s++)
+        if (cudaEventCreateWithFlags(&ctx->ev_entropy[s], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_exec[s], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
     *out = ctx;
     return CZS_OK;
 }
@@ -62,8 +67,15 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p); cudaFree(ctx->blocks.p); cudaFree(ctx->huf_items.p);
-    cudaFree(ctx->fse_items.p); cudaFree(ctx->lit.p); cudaFree(ctx->seq.p); cudaFree(ctx->counters.p);
+    cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p);
+    for (int s = 0; s < 2; s++) {
+        cudaFree(ctx->blocks[s].p); cudaFree(ctx->huf_items[s].p); cudaFree(ctx->fse_items[s].p); cudaFree(ctx->lit[s].p);
+        cudaFree(ctx->seq[s].p); cudaFree(ctx->counters[s].p);
+        if (ctx->ev_entropy[s]) cudaEventDestroy(ctx->ev_entropy[s]);
+        if (ctx->ev_exec[s]) cudaEventDestroy(ctx->ev_exec[s]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->exec_stream) cudaStreamDestroy(ctx->exec_stream);
     cudaFree(ctx->h_descs.p); cudaFree(ctx->h_results.p);
     for (int s = 0; s < 2; s++) { cudaFree(ctx->h_src[s].p); cudaFree(ctx->h_dst[s].p); }
     if (ctx->totals_h) cudaFreeHost(ctx->totals_h);
@@ -124,7 +136,6 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
     int rc;
     if ((rc = ensure(ctx, ctx->infos, n))) return rc;
     if ((rc = ensure(ctx, ctx->totals_d, kMaxWaves))) return rc;
-    if ((rc = ensure(ctx, ctx->counters, 1))) return rc;
 
     // ---- plan: scan every frame, then size waves so that scratch fits the budget ----
     uint64_t W = std::min<uint64_t>((n + 127) / 128 * 128, ctx->wave_frames);
@@ -142,7 +153,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         CZB_CUDA(ctx, cudaStreamSynchronize(stream));
         uint64_t worst = 0;
         for (uint64_t w = 0; w < n_waves; w++) worst = std::max(worst, wave_scratch_bytes(ctx->totals_h[w]));
-        if (worst <= ctx->budget || W <= 128 || (n + W / 2 - 1) / (W / 2) > kMaxWaves) break;
+        if (2 * worst <= ctx->budget || W <= 128 || (n + W / 2 - 1) / (W / 2) > kMaxWaves) break;
         W = std::max<uint64_t>(128, (W / 2 + 127) / 128 * 128);
     }
     WaveTotals mx{};
@@ -152,23 +163,47 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         mx.n_seq = std::max(mx.n_seq, t.n_seq); mx.n_huf = std::max(mx.n_huf, t.n_huf); mx.n_fse = std::max(mx.n_fse, t.n_fse);
         if (t.n_blocks > 0xFFFFFF00ull) { ctx->last_error = "too many blocks in one wave"; return CZS_UNSUPPORTED; }
     }
-    if ((rc = ensure(ctx, ctx->blocks, mx.n_blocks + 1))) return rc;
-    if ((rc = ensure(ctx, ctx->huf_items, mx.n_huf + 1))) return rc;
-    if ((rc = ensure(ctx, ctx->fse_items, mx.n_fse + 1))) return rc;
-    if ((rc = ensure(ctx, ctx->lit, mx.lit_bytes + 64))) return rc;
-    if ((rc = ensure(ctx, ctx->seq, mx.n_seq + 1))) return rc;
+    const int n_sets = n_waves > 1 ? 2 : 1;
+    for (int s = 0; s < n_sets; s++) {
+        if ((rc = ensure(ctx, ctx->counters[s], 1))) return rc;
+        if ((rc = ensure(ctx, ctx->blocks[s], mx.n_blocks + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->huf_items[s], mx.n_huf + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->fse_items[s], mx.n_fse + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->lit[s], mx.lit_bytes + 64))) return rc;
+        if ((rc = ensure(ctx, ctx->seq[s], mx.n_seq + 2))) return rc;
+    }
 
     { ProfScope ps(ctx, stream, 6); launch_header_results(lc, ctx->infos.p, results, n); }
+    // Two-stage pipeline over waves: the entropy stage (fill, Huffman, FSE: shared-memory bound, few
+    // warps per SM) runs on `stream`; sequence execution (many warps, almost no shared memory) runs
+    // on exec_stream and overlaps the entropy stage of the next wave.  Scratch is double-buffered.
+    cudaStream_t xs = n_waves > 1 ? ctx->exec_stream : stream;
+    LaunchCtx lx{xs, &ctx->launches};
+    if (n_waves > 1) {
+        CZB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, stream));
+        CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_fork, 0));
+    }
     for (uint64_t w = 0; w < n_waves; w++) {
+        const int s = (int)(w & 1);
         const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
         const WaveTotals& t = ctx->totals_h[w];
-        CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters.p, 0, sizeof(WaveCounters), stream));
-        { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->huf_items.p, ctx->fse_items.p, ctx->counters.p); }
-        { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks.p, ctx->huf_items.p, ctx->counters.p, (uint32_t)t.n_huf, ctx->lit.p); }
-        { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks.p, ctx->fse_items.p, ctx->counters.p, (uint32_t)t.n_fse, ctx->seq.p); }
-        { ProfScope ps(ctx, stream, 4); launch_exec(lc, descs, ctx->infos.p, first, count, ctx->blocks.p, ctx->lit.p, ctx->seq.p, results); }
-        if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, stream, 5); launch_xxh64(lc, descs, results, first, count); }
-        ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count;
+        if (w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
+        CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
+        { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p); }
+        { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p); }
+        { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks[s].p, ctx->fse_items[s].p, ctx->counters[s].p, (uint32_t)t.n_fse, ctx->seq[s].p); }
+        if (n_waves > 1) {
+            CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));
+            CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
+        }
+        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
+        if (n_waves > 1) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
+        ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;
+    }
+    if (n_waves > 1) {  // join: later work on `stream` sees every result
+        CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 1) & 1], 0));
+        if (n_waves > 1) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 2) & 1], 0));
     }
     CZB_CUDA(ctx, cudaGetLastError());
     return CZS_OK;
@@ -364,7 +399,7 @@ extern "C" int czb_debug_copy_blocks(czb_context* ctx, czb_debug_block* out, uin
     CZB_CUDA(ctx, cudaDeviceSynchronize());
     const uint64_t nb = std::min<uint64_t>(cap, ctx->last_wave.n_blocks);
     std::vector<BlockDesc> h(nb);
-    if (nb) CZB_CUDA(ctx, cudaMemcpy(h.data(), ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost));
+    if (nb) CZB_CUDA(ctx, cudaMemcpy(h.data(), ctx->blocks[ctx->last_set].p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < nb; i++) {
         const BlockDesc& d = h[i];
         czb_debug_block& o = out[i];
@@ -385,7 +420,7 @@ extern "C" int czb_debug_copy_literals(czb_context* ctx, uint8_t* out, uint64_t 
     CZB_CUDA(ctx, cudaSetDevice(ctx->device));
     CZB_CUDA(ctx, cudaDeviceSynchronize());
     const uint64_t nbytes = std::min<uint64_t>(cap, ctx->last_wave.lit_bytes);
-    if (nbytes) CZB_CUDA(ctx, cudaMemcpy(out, ctx->lit.p, nbytes, cudaMemcpyDeviceToHost));
+    if (nbytes) CZB_CUDA(ctx, cudaMemcpy(out, ctx->lit[ctx->last_set].p, nbytes, cudaMemcpyDeviceToHost));
     return CZS_OK;
 }
 extern "C" int czb_debug_copy_sequences(czb_context* ctx, uint32_t* out, uint64_t cap_seqs) {
@@ -394,7 +429,7 @@ extern "C" int czb_debug_copy_sequences(czb_context* ctx, uint32_t* out, uint64_
     CZB_CUDA(ctx, cudaDeviceSynchronize());
     const uint64_t ns = std::min<uint64_t>(cap_seqs, ctx->last_wave.n_seq);
     std::vector<Seq> h(ns);
-    if (ns) CZB_CUDA(ctx, cudaMemcpy(h.data(), ctx->seq.p, ns * sizeof(Seq), cudaMemcpyDeviceToHost));
+    if (ns) CZB_CUDA(ctx, cudaMemcpy(h.data(), ctx->seq[ctx->last_set].p, ns * sizeof(Seq), cudaMemcpyDeviceToHost));
     for (uint64_t i = 0; i < ns; i++) {
         out[3 * i] = seq_ll(h[i]); out[3 * i + 1] = seq_ml(h[i]);
         const uint32_t f = seq_off29(h[i]);

@@ -147,7 +147,7 @@ static int fd_run_device(czb_frame_decoder* fd) {
     // per-block records
     const uint64_t nb = ctx->last_wave.n_blocks;
     std::vector<BlockDesc> bd(nb);
-    if (nb) FD_CUDA(fd, cudaMemcpy(bd.data(), ctx->blocks.p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost));
+    if (nb) FD_CUDA(fd, cudaMemcpy(bd.data(), ctx->blocks[ctx->last_set].p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost));
     fd->blocks.clear();
     uint64_t produced = 0;
     bool complete = false;

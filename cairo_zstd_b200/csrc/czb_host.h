@@ -28,11 +28,15 @@ struct czb_context {
     DevBuf<czb::FrameInfo> infos;
     DevBuf<czb::WaveTotals> totals_d;
     czb::WaveTotals* totals_h = nullptr;  // pinned
-    DevBuf<czb::WaveCounters> counters;
-    DevBuf<czb::BlockDesc> blocks;
-    DevBuf<uint32_t> huf_items, fse_items;
-    DevBuf<uint8_t> lit;
-    DevBuf<czb::Seq> seq;
+    // per-wave scratch, double-buffered: the entropy stage of wave w+1 overlaps sequence execution of wave w
+    DevBuf<czb::WaveCounters> counters[2];
+    DevBuf<czb::BlockDesc> blocks[2];
+    DevBuf<uint32_t> huf_items[2], fse_items[2];
+    DevBuf<uint8_t> lit[2];
+    DevBuf<czb::Seq> seq[2];
+    cudaStream_t exec_stream = nullptr;
+    cudaEvent_t ev_entropy[2] = {nullptr, nullptr}, ev_exec[2] = {nullptr, nullptr}, ev_fork = nullptr;
+    int last_set = 0;
 
     // staging for the host-pointer entry points
     DevBuf<uint8_t> h_src[2], h_dst[2];

@@ -23,16 +23,17 @@
 namespace czb {
 
 constexpr int EXEC_WARPS = 4;
+#ifndef EXEC_CTAS_PER_SM
+#define EXEC_CTAS_PER_SM 6
+#endif
 constexpr uint32_t EXEC_ROW = 128;
 
 struct ExecWarpSmem {
     uint32_t bound[66];      // bound[2i] = first output byte of sequence i's literal run, [2i+1] = of its match, [64] = span
-    uint32_t segdelta[64];   // per segment: bit 31 = per-byte path, bit 30 = literal, low 30 bits = signed source delta
+    int segdelta[64];        // per segment: source index = output position + delta (literal buffer for even ids, dst for odd)
     __align__(4) uint8_t rowmap[EXEC_ROW];  // (segment id + 1) at each non-empty segment's start byte inside the row
     __align__(4) uint8_t krow[EXEC_ROW];    // (segment id + 1) owning each row byte
 };
-
-__device__ __forceinline__ int seg_sdelta(uint32_t d) { return ((int)(d << 2)) >> 2; }
 
 // dst[0..n) = src[0..n): 16-byte stores to aligned dst; src may have any alignment (aligned
 // 32-bit loads + funnel shifts).  Only aligned words containing at least one source byte are read.
@@ -77,17 +78,18 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
     for (uint32_t i = lane; i < n; i += 32) dst[i] = byte;
 }
 
-__global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
+__global__ void __launch_bounds__(EXEC_WARPS * 32, 6) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
                                                            uint64_t count, BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
     __shared__ ExecWarpSmem smem[EXEC_WARPS];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
-    const uint64_t f = (uint64_t)blockIdx.x * EXEC_WARPS + warp;
-    if (f >= count) return;
     ExecWarpSmem& sm = smem[warp];
+    // Persistent warps: the grid is a fixed number of CTAs per SM (so that the shared-memory-heavy
+    // entropy kernels of the next wave can co-reside), each warp strides over the wave's frames.
+    for (uint64_t f = (uint64_t)blockIdx.x * EXEC_WARPS + warp; f < count; f += (uint64_t)gridDim.x * EXEC_WARPS) {
     const FrameInfo fi = infos[f];
-    if (fi.status != CZS_OK) return;  // k_header_results already reported it
+    if (fi.status != CZS_OK) continue;  // k_header_results already reported it
     const czb_frame_desc fd = descs[f];
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
@@ -126,11 +128,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
             uint32_t lit_pos = 0;
             __syncwarp();
             const Seq* seqs = seq_scratch + d.seq_off;
+            Seq rec_next = lane < d.n_seq ? seqs[lane] : 0ull;
             for (uint32_t s0 = 0; s0 < d.n_seq; s0 += 32) {
                 const uint32_t i = s0 + lane;
                 const bool have = i < d.n_seq;
+                const Seq rec = rec_next;
+                if (i + 32 < d.n_seq) rec_next = seqs[i + 32];  // next chunk's record is in flight while this chunk executes
                 uint32_t ll = 0, ml = 0, off = 1;
-                if (have) { const Seq q = seqs[i]; ll = seq_ll(q); ml = seq_ml(q); off = off29_resolve(seq_off29(q), h0, h1, h2); }
+                if (have) { ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
                 // warp prefix sums: literal offsets and output offsets (u32 cannot wrap: 32 * (131071 + 131074) < 2^32)
                 uint32_t lsum = ll, osum = ll + ml;
 #pragma unroll
@@ -156,9 +161,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
                 // publish the 64 segments of this chunk
                 const uint32_t segA = my_out, segM = my_out + ll;
                 sm.bound[2 * lane] = segA; sm.bound[2 * lane + 1] = segM;
-                sm.segdelta[2 * lane] = ((my_lit - segA) & 0x3FFFFFFFu) | 0x40000000u | (lit_rle ? 0x80000000u : 0u);
-                sm.segdelta[2 * lane + 1] = ((0u - off) & 0x3FFFFFFFu) | ((off < ml || off < EXEC_ROW) ? 0x80000000u : 0u);
+                sm.segdelta[2 * lane] = (int)my_lit - (int)segA;
+                sm.segdelta[2 * lane + 1] = -(int)off;
                 if (lane == 0) sm.bound[64] = span;
+                const uint32_t wrapmask = __ballot_sync(0xFFFFFFFFu, have && off < ml);  // overlapping matches
                 uint8_t* obase = dst + out;
                 const int a = (int)(reinterpret_cast<uintptr_t>(obase) & 3);
                 uint32_t carry = 0;
@@ -183,19 +189,21 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
                     __syncwarp();
                     // ---- gather the four bytes of this lane's word ----
                     const int p0 = r + 4 * (int)lane;
+                    const int rlo = r > 0 ? r : 0;  // sources at or beyond this position are being built in this row
                     uint32_t word = 0, slow_mask = 0;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int p = p0 + j;
                         const bool valid = (uint32_t)p < span;
-                        const uint32_t kj = (x >> (8 * j)) & 0xFFu;
-                        const uint32_t d = sm.segdelta[kj ? kj - 1 : 0];
-                        const uint8_t* base = (d & 0x40000000u) ? lits : obase;
-                        const bool fast = valid && !(d >> 31);
+                        const uint32_t kseg = ((x >> (8 * j)) & 0xFFu) - 1u;
+                        const int q = p + (valid ? sm.segdelta[kseg & 63u] : 0);
+                        const bool is_match = kseg & 1u;
+                        const bool slow = is_match ? (q >= rlo || ((wrapmask >> ((kseg >> 1) & 31u)) & 1u)) : lit_rle;
+                        const uint8_t* base = is_match ? obase : lits;
                         uint32_t b = 0;
-                        if (fast) b = base[(int64_t)p + seg_sdelta(d)];
+                        if (valid && !slow) b = base[q];
                         word |= b << (8 * j);
-                        if (valid && (d >> 31)) slow_mask |= 1u << j;
+                        if (valid && slow) slow_mask |= 1u << j;
                     }
                     if (__any_sync(0xFFFFFFFFu, slow_mask != 0)) {
                         for (int j = 0; j < 4; j++) {
@@ -203,15 +211,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
                             int p = p0 + j;
                             uint32_t kq = ((x >> (8 * j)) & 0xFFu) - 1u, byte;
                             for (;;) {
-                                const uint32_t d = sm.segdelta[kq];
-                                const int sd = seg_sdelta(d);
-                                if (d & 0x40000000u) { byte = lit_rle ? rle_byte : lits[p + sd]; break; }
-                                const uint32_t o = (uint32_t)(-sd), seg0 = sm.bound[kq];
+                                const int dlt = sm.segdelta[kq];
+                                if (!(kq & 1u)) { byte = lit_rle ? rle_byte : lits[p + dlt]; break; }
+                                const uint32_t o = (uint32_t)(-dlt), seg0 = sm.bound[kq];
                                 uint32_t rel = (uint32_t)p - seg0;
                                 if (rel >= o) rel %= o;  // overlapping match = periodic pattern (decode_buffer.cairo:101-120)
                                 const int q = (int)seg0 + (int)rel - (int)o;  // chunk-relative source position
-                                if (q < r || q < 0) { byte = obase[q]; break; }  // earlier rows / chunks are already in dst
-                                kq = (uint32_t)sm.krow[q - r] - 1u;            // same row, strictly earlier byte: chase
+                                if (q < rlo) { byte = obase[q]; break; }       // earlier rows / chunks are already in dst
+                                kq = (uint32_t)sm.krow[q - r] - 1u;             // same row, strictly earlier byte: chase
                                 p = q;
                             }
                             word |= byte << (8 * j);
@@ -265,12 +272,26 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32) k_exec(const czb_frame_desc* 
         r.finished = (status == CZS_OK && finished && (!((fi.descriptor >> 2) & 1) || fi.has_checksum)) ? 1 : 0;
         results[f] = r;
     }
+    __syncwarp();
+    }  // frame loop
+}
+
+static int exec_persistent_ctas() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        n = sms * EXEC_CTAS_PER_SM;
+    }
+    return n;
 }
 
 void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count,
                  BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
     if (!count) return;
-    const unsigned grid = (unsigned)((count + EXEC_WARPS - 1) / EXEC_WARPS);
+    const uint64_t want = (count + EXEC_WARPS - 1) / EXEC_WARPS;
+    const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
     k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, blocks, lit_scratch, seq_scratch, results + first);
     ++*lc.launches;
 }

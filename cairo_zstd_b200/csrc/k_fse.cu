@@ -8,10 +8,10 @@
 // chain over the same sequences.
 //
 // Mapping: the interleaved LL/OF/ML state machine is one dependency chain per block and cannot be
-// split, so parallelism comes from blocks: a CTA owns 27 blocks, its 4 warps build the 81 tables
+// split, so parallelism comes from blocks: a CTA owns 25 blocks, its 4 warps build the 75 tables
 // cooperatively, then warp 0 decodes with lane = block.  Throughput is bounded by
 // (blocks resident per SM) / (chain latency per sequence); 16-bit table entries (czb_fse_build.cuh)
-// keep a block's three tables at <= 2.5 KiB so 81 blocks fit per SM (three CTAs).  HBM traffic: the
+// keep a block's three tables at <= 2.5 KiB so 75 blocks fit per SM (three CTAs).  HBM traffic: the
 // bitstream in (a few bytes per sequence) and one packed 8-byte record per sequence out to scratch.
 #include <type_traits>
 
@@ -21,7 +21,8 @@
 namespace czb {
 
 constexpr int FSE_WARPS = 4;
-constexpr int FSE_SLOTS = 27;  // 27 * 2560 B of tables + scratch = ~75 KB -> three CTAs (81 decode lanes) per SM
+constexpr int FSE_SLOTS = 25;  // 25 * 2560 B of tables + scratch = ~70 KB -> three CTAs (75 decode lanes) per SM, leaving ~17 KB of
+                               // shared memory so k_exec CTAs of the previous wave can co-reside (they use the idle issue slots)
 constexpr int FSE_SLOT_ENTRIES = 512 + 512 + 256;  // LL (log<=9), ML (log<=9), OF (log<=8)
 constexpr int FSE_LL_OFS = 0, FSE_ML_OFS = 512, FSE_OF_OFS = 1024;
 
@@ -71,7 +72,7 @@ __device__ inline bool skip_description(int mode, int s, const uint8_t* p, int l
     return true;
 }
 
-__global__ void __launch_bounds__(FSE_WARPS * 32) k_fse(const czb_frame_desc* __restrict__ descs, BlockDesc* __restrict__ blocks,
+__global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc* __restrict__ descs, BlockDesc* __restrict__ blocks,
                                                          const uint32_t* __restrict__ items,
                                                          const WaveCounters* __restrict__ counters, Seq* __restrict__ seq_scratch) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
