@@ -2,6 +2,7 @@
 // (The FrameDecoder handle mirror lives in czb_handle.cu.)
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,6 +49,7 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     ctx->device = device;
     ctx->budget = budget ? budget : (8ull << 30);
     ctx->wave_frames = 65536;
+    ctx->no_overlap = getenv("CZB_NO_OVERLAP") != nullptr;  // measurement aid: run every kernel alone
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
     if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0) { delete ctx; return CZS_CUDA_ERROR; }
     if (cudaMallocHost(reinterpret_cast<void**>(&ctx->totals_h), sizeof(WaveTotals) * kMaxWaves) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
@@ -69,6 +71,7 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p);
     for (int s = 0; s < 2; s++) {
+        cudaFree(ctx->huf_cls0[s].p); cudaFree(ctx->huf_cls1[s].p); cudaFree(ctx->huf_recs[s].p);
         cudaFree(ctx->blocks[s].p); cudaFree(ctx->huf_items[s].p); cudaFree(ctx->fse_items[s].p); cudaFree(ctx->lit[s].p);
         cudaFree(ctx->seq[s].p); cudaFree(ctx->counters[s].p);
         if (ctx->ev_entropy[s]) cudaEventDestroy(ctx->ev_entropy[s]);
@@ -121,7 +124,7 @@ extern "C" int czb_profile_collect(czb_context* ctx, double* ms, uint64_t* launc
 }
 
 static uint64_t wave_scratch_bytes(const WaveTotals& t) {
-    return t.n_blocks * sizeof(BlockDesc) + t.lit_bytes + t.n_seq * sizeof(Seq) + (t.n_huf + t.n_fse) * 4;
+    return t.n_blocks * sizeof(BlockDesc) + t.lit_bytes + t.n_seq * sizeof(Seq) + (t.n_huf + t.n_fse) * 4 + t.n_huf * (sizeof(HufRec) + 8);
 }
 
 // The hot path.  descs/results are device arrays.
@@ -168,6 +171,9 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         if ((rc = ensure(ctx, ctx->counters[s], 1))) return rc;
         if ((rc = ensure(ctx, ctx->blocks[s], mx.n_blocks + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_items[s], mx.n_huf + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->huf_cls0[s], mx.n_huf + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->huf_cls1[s], mx.n_huf + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->huf_recs[s], mx.n_huf + 1))) return rc;
         if ((rc = ensure(ctx, ctx->fse_items[s], mx.n_fse + 1))) return rc;
         if ((rc = ensure(ctx, ctx->lit[s], mx.lit_bytes + 64))) return rc;
         if ((rc = ensure(ctx, ctx->seq[s], mx.n_seq + 2))) return rc;
@@ -177,9 +183,10 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
     // Two-stage pipeline over waves: the entropy stage (fill, Huffman, FSE: shared-memory bound, few
     // warps per SM) runs on `stream`; sequence execution (many warps, almost no shared memory) runs
     // on exec_stream and overlaps the entropy stage of the next wave.  Scratch is double-buffered.
-    cudaStream_t xs = n_waves > 1 ? ctx->exec_stream : stream;
+    const bool overlap = n_waves > 1 && !ctx->no_overlap;
+    cudaStream_t xs = overlap ? ctx->exec_stream : stream;
     LaunchCtx lx{xs, &ctx->launches};
-    if (n_waves > 1) {
+    if (overlap) {
         CZB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, stream));
         CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_fork, 0));
     }
@@ -187,21 +194,21 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         const int s = (int)(w & 1);
         const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
         const WaveTotals& t = ctx->totals_h[w];
-        if (w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
+        if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
         { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p); }
-        { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p); }
+        { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p, ctx->huf_recs[s].p, ctx->huf_cls0[s].p, ctx->huf_cls1[s].p); }
         { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks[s].p, ctx->fse_items[s].p, ctx->counters[s].p, (uint32_t)t.n_fse, ctx->seq[s].p); }
-        if (n_waves > 1) {
+        if (overlap) {
             CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
-        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, ctx->counters[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
-        if (n_waves > 1) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
+        if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;
     }
-    if (n_waves > 1) {  // join: later work on `stream` sees every result
+    if (overlap) {  // join: later work on `stream` sees every result
         CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 1) & 1], 0));
         if (n_waves > 1) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 2) & 1], 0));
     }

@@ -31,12 +31,14 @@ struct czb_context {
     // per-wave scratch, double-buffered: the entropy stage of wave w+1 overlaps sequence execution of wave w
     DevBuf<czb::WaveCounters> counters[2];
     DevBuf<czb::BlockDesc> blocks[2];
-    DevBuf<uint32_t> huf_items[2], fse_items[2];
+    DevBuf<uint32_t> huf_items[2], fse_items[2], huf_cls0[2], huf_cls1[2];
+    DevBuf<czb::HufRec> huf_recs[2];
     DevBuf<uint8_t> lit[2];
     DevBuf<czb::Seq> seq[2];
     cudaStream_t exec_stream = nullptr;
     cudaEvent_t ev_entropy[2] = {nullptr, nullptr}, ev_exec[2] = {nullptr, nullptr}, ev_fork = nullptr;
     int last_set = 0;
+    bool no_overlap = false;
 
     // staging for the host-pointer entry points
     DevBuf<uint8_t> h_src[2], h_dst[2];

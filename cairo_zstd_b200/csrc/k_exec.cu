@@ -30,7 +30,10 @@ constexpr uint32_t EXEC_ROW = 128;
 
 struct ExecWarpSmem {
     uint32_t bound[66];      // bound[2i] = first output byte of sequence i's literal run, [2i+1] = of its match, [64] = span
-    int segdelta[64];        // per segment: source index = output position + delta (literal buffer for even ids, dst for odd)
+    int segdelta[66];        // per segment: source index = output position + delta (literal buffer for even ids, dst for odd);
+                             // [64] is the "past the end" pseudo segment
+    unsigned long long segbase[66];  // indexed by id = segment index + 1: address of the source byte for output position 0
+    uint32_t segthr[66];     // indexed by id: a byte at row-relative... see gather: fast iff (p - rlo) < segthr[id]
     __align__(4) uint8_t rowmap[EXEC_ROW];  // (segment id + 1) at each non-empty segment's start byte inside the row
     __align__(4) uint8_t krow[EXEC_ROW];    // (segment id + 1) owning each row byte
 };
@@ -79,15 +82,19 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
 }
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, 6) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
-                                                           uint64_t count, BlockDesc* __restrict__ blocks,
+                                                           uint64_t count, WaveCounters* __restrict__ counters, BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
     __shared__ ExecWarpSmem smem[EXEC_WARPS];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     ExecWarpSmem& sm = smem[warp];
-    // Persistent warps: the grid is a fixed number of CTAs per SM (so that the shared-memory-heavy
-    // entropy kernels of the next wave can co-reside), each warp strides over the wave's frames.
-    for (uint64_t f = (uint64_t)blockIdx.x * EXEC_WARPS + warp; f < count; f += (uint64_t)gridDim.x * EXEC_WARPS) {
+    // Persistent warps pulling frames from a queue: frames differ in size by orders of magnitude
+    // (1 KiB .. tens of MiB), so a static frame -> warp map would leave most warps idle at the tail.
+    for (;;) {
+    unsigned int fq = 0;
+    if (lane == 0) fq = atomicAdd(&counters->exec_next, 1u);
+    const uint64_t f = __shfl_sync(0xFFFFFFFFu, fq, 0);
+    if (f >= count) break;
     const FrameInfo fi = infos[f];
     if (fi.status != CZS_OK) continue;  // k_header_results already reported it
     const czb_frame_desc fd = descs[f];
@@ -163,9 +170,20 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 6) k_exec(const czb_frame_des
                 sm.bound[2 * lane] = segA; sm.bound[2 * lane + 1] = segM;
                 sm.segdelta[2 * lane] = (int)my_lit - (int)segA;
                 sm.segdelta[2 * lane + 1] = -(int)off;
-                if (lane == 0) sm.bound[64] = span;
-                const uint32_t wrapmask = __ballot_sync(0xFFFFFFFFu, have && off < ml);  // overlapping matches
                 uint8_t* obase = dst + out;
+                // gather tables, indexed by id = segment index + 1 (0 = before the chunk, 65 = past the end):
+                // source address of output position p is segbase[id] + p; the byte may be fetched directly iff
+                // (p - rlo) < segthr[id]: always for literals, only while the source precedes the row for matches,
+                // never for overlapping matches and RLE literals (those take the per-byte path).
+                sm.segbase[2 * lane + 1] = (unsigned long long)(lits + my_lit) - segA;
+                sm.segbase[2 * lane + 2] = (unsigned long long)obase - off;
+                sm.segthr[2 * lane + 1] = lit_rle ? 0u : 0xFFFFFFFFu;
+                sm.segthr[2 * lane + 2] = off < ml ? 0u : off;
+                if (lane == 0) {
+                    sm.bound[64] = span;
+                    sm.segbase[0] = sm.segbase[65] = (unsigned long long)obase; sm.segthr[0] = sm.segthr[65] = 0u;
+                }
+                const uint32_t wrapmask = __ballot_sync(0xFFFFFFFFu, have && off < ml);  // overlapping matches
                 const int a = (int)(reinterpret_cast<uintptr_t>(obase) & 3);
                 uint32_t carry = 0;
                 for (int r = -a; r < (int)span; r += (int)EXEC_ROW) {
@@ -174,6 +192,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 6) k_exec(const czb_frame_des
                     __syncwarp();
                     if (ll && (uint32_t)((int)segA - r) < EXEC_ROW) sm.rowmap[(int)segA - r] = (uint8_t)(2 * lane + 1);
                     if (ml && (uint32_t)((int)segM - r) < EXEC_ROW) sm.rowmap[(int)segM - r] = (uint8_t)(2 * lane + 2);
+                    if (lane == 0 && (uint32_t)((int)span - r) < EXEC_ROW) sm.rowmap[(int)span - r] = 65;  // pseudo segment: past the end
                     __syncwarp();
                     uint32_t x = *reinterpret_cast<const uint32_t*>(&sm.rowmap[4 * lane]);
                     x = __vmaxu4(x, x << 8);
@@ -189,21 +208,21 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 6) k_exec(const czb_frame_des
                     __syncwarp();
                     // ---- gather the four bytes of this lane's word ----
                     const int p0 = r + 4 * (int)lane;
-                    const int rlo = r > 0 ? r : 0;  // sources at or beyond this position are being built in this row
+                    const int rlo = r > 0 ? r : 0;  // match sources at or beyond this position are being built in this row
+                    const uint32_t pr0 = (uint32_t)(p0 - rlo);
                     uint32_t word = 0, slow_mask = 0;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const int p = p0 + j;
-                        const bool valid = (uint32_t)p < span;
-                        const uint32_t kseg = ((x >> (8 * j)) & 0xFFu) - 1u;
-                        const int q = p + (valid ? sm.segdelta[kseg & 63u] : 0);
-                        const bool is_match = kseg & 1u;
-                        const bool slow = is_match ? (q >= rlo || ((wrapmask >> ((kseg >> 1) & 31u)) & 1u)) : lit_rle;
-                        const uint8_t* base = is_match ? obase : lits;
+                        const uint32_t kj = (x >> (8 * j)) & 0xFFu;
+                        const unsigned long long bs = sm.segbase[kj];
+                        const uint32_t thr = sm.segthr[kj];
+                        const uint32_t pj = (uint32_t)(p0 + j);
+                        const bool valid = pj < span;
+                        const bool fast = (pr0 + (uint32_t)j) < thr;
                         uint32_t b = 0;
-                        if (valid && !slow) b = base[q];
+                        if (valid && fast) b = *reinterpret_cast<const uint8_t*>(bs + pj);
                         word |= b << (8 * j);
-                        if (valid && slow) slow_mask |= 1u << j;
+                        if (valid && !fast) slow_mask |= 1u << j;
                     }
                     if (__any_sync(0xFFFFFFFFu, slow_mask != 0)) {
                         for (int j = 0; j < 4; j++) {
@@ -213,12 +232,13 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, 6) k_exec(const czb_frame_des
                             for (;;) {
                                 const int dlt = sm.segdelta[kq];
                                 if (!(kq & 1u)) { byte = lit_rle ? rle_byte : lits[p + dlt]; break; }
-                                const uint32_t o = (uint32_t)(-dlt), seg0 = sm.bound[kq];
-                                uint32_t rel = (uint32_t)p - seg0;
-                                if (rel >= o) rel %= o;  // overlapping match = periodic pattern (decode_buffer.cairo:101-120)
-                                const int q = (int)seg0 + (int)rel - (int)o;  // chunk-relative source position
-                                if (q < rlo) { byte = obase[q]; break; }       // earlier rows / chunks are already in dst
-                                kq = (uint32_t)sm.krow[q - r] - 1u;             // same row, strictly earlier byte: chase
+                                int q = p + dlt;  // p - offset
+                                if ((wrapmask >> (kq >> 1)) & 1u) {  // overlapping match = periodic pattern (decode_buffer.cairo:101-120)
+                                    const uint32_t o = (uint32_t)(-dlt), seg0 = sm.bound[kq];
+                                    q = (int)seg0 + (int)(((uint32_t)p - seg0) % o) - (int)o;
+                                }
+                                if (q < rlo) { byte = obase[q]; break; }  // earlier rows / chunks are already in dst
+                                kq = (uint32_t)sm.krow[q - r] - 1u;        // same row, strictly earlier byte: chase
                                 p = q;
                             }
                             word |= byte << (8 * j);
@@ -288,11 +308,11 @@ static int exec_persistent_ctas() {
 }
 
 void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count,
-                 BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
+                 WaveCounters* counters, BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
     if (!count) return;
     const uint64_t want = (count + EXEC_WARPS - 1) / EXEC_WARPS;
     const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
-    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, blocks, lit_scratch, seq_scratch, results + first);
+    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, counters, blocks, lit_scratch, seq_scratch, results + first);
     ++*lc.launches;
 }
 
