@@ -407,8 +407,9 @@ def run_e2e(args, ctx, frames, origs, flens, n_dev_frames, dev, dist, torch):
     value = float(b.item()) * args.e2e_steps / dt_max / 1e9
     for a in (h_src, h_dst, h_res):
         cudart.cudaHostUnregister(a.ctypes.data)
-    return {"value": value, "unit": "GB/s", "h2d_bytes_per_step": int(src_off[-1]), "d2h_bytes_per_step": int(n * FRAME_SIZE),
-            "frames_per_step": int(n), "steps": args.e2e_steps, "ms_per_step": 1e3 * dt_max / args.e2e_steps,
+    world = dist.get_world_size() if dist is not None else 1
+    return {"value": value, "unit": "GB/s", "h2d_bytes_per_step": int(src_off[-1]) * world, "d2h_bytes_per_step": int(n * FRAME_SIZE) * world,
+            "frames_per_step": int(n) * world, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt_max / args.e2e_steps,
             "timing": "host wall clock around czb_decode_batch_host_packed (it returns when outputs are in host memory)",
             "pin_seconds": pin_s,
             "note": "pinned host buffers; frame count bounded by host RAM" if n < n_dev_frames else "pinned host buffers; full workload"}

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -49,10 +50,15 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     ctx->device = device;
     ctx->budget = budget ? budget : (8ull << 30);
     ctx->wave_frames = 65536;
-    ctx->no_overlap = getenv("CZB_NO_OVERLAP") != nullptr;  // measurement aid: run every kernel alone
+    ctx->no_overlap = getenv("CZB_NO_OVERLAP") != nullptr;
+    if (const char* e = getenv("CZB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (uint64_t)atoll(e) << 20;  // measurement aid: run every kernel alone
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
     if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0) { delete ctx; return CZS_CUDA_ERROR; }
-    if (cudaMallocHost(reinterpret_cast<void**>(&ctx->totals_h), sizeof(WaveTotals) * kMaxWaves) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    // Planning read-back buffer: host memory mapped into the device address space.  A kernel writes the
+    // per-wave totals straight into it, so the read-back never queues behind a large device-to-host
+    // copy on the copy engine (that serialised decode behind the previous chunk's output transfer).
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->totals_h), sizeof(WaveTotals) * kMaxWaves, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->totals_h_dev), ctx->totals_h, 0) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
     if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess ||
@@ -80,7 +86,7 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->exec_stream) cudaStreamDestroy(ctx->exec_stream);
     cudaFree(ctx->h_descs.p); cudaFree(ctx->h_results.p);
-    for (int s = 0; s < 2; s++) { cudaFree(ctx->h_src[s].p); cudaFree(ctx->h_dst[s].p); }
+    for (int s = 0; s < czb_context::kHostSlots; s++) { cudaFree(ctx->h_src[s].p); cudaFree(ctx->h_dst[s].p); }
     if (ctx->totals_h) cudaFreeHost(ctx->totals_h);
     if (ctx->pin_a) cudaFreeHost(ctx->pin_a);
     if (ctx->pin_b) cudaFreeHost(ctx->pin_b);
@@ -152,7 +158,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         } else {
             launch_wave_totals(lc, ctx->infos.p, n, W, ctx->totals_d.p, n_waves);
         }
-        CZB_CUDA(ctx, cudaMemcpyAsync(ctx->totals_h, ctx->totals_d.p, n_waves * sizeof(WaveTotals), cudaMemcpyDeviceToHost, stream));
+        launch_publish_totals(lc, ctx->totals_d.p, ctx->totals_h_dev, n_waves);
         CZB_CUDA(ctx, cudaStreamSynchronize(stream));
         uint64_t worst = 0;
         for (uint64_t w = 0; w < n_waves; w++) worst = std::max(worst, wave_scratch_bytes(ctx->totals_h[w]));
@@ -300,27 +306,36 @@ extern "C" int czb_decode_batch_host_packed(czb_context* ctx, const uint8_t* src
         max_frames = std::max(max_frames, cuts[c + 1] - cuts[c]);
     }
     int rc;
-    for (int s = 0; s < 2; s++) {
+    constexpr int NS = czb_context::kHostSlots;
+    for (int s = 0; s < NS; s++) {
         if ((rc = ensure(ctx, ctx->h_src[s], max_src + 64))) return rc;
         if ((rc = ensure(ctx, ctx->h_dst[s], max_dst + 64))) return rc;
     }
-    if ((rc = ensure(ctx, ctx->h_descs, 2 * max_frames))) return rc;
-    if ((rc = ensure(ctx, ctx->h_results, 2 * max_frames))) return rc;
-    if ((rc = ensure_pinned(ctx, ctx->pin_b, ctx->pin_b_cap, 2 * max_frames * sizeof(czb_frame_desc)))) return rc;
-    cudaEvent_t ev_in[2], ev_dec[2], ev_out[2];
-    for (int s = 0; s < 2; s++) {
+    if ((rc = ensure(ctx, ctx->h_descs, NS * max_frames))) return rc;
+    if ((rc = ensure(ctx, ctx->h_results, NS * max_frames))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->pin_b, ctx->pin_b_cap, NS * max_frames * sizeof(czb_frame_desc)))) return rc;
+    cudaEvent_t ev_in[NS], ev_dec[NS], ev_out[NS];
+    for (int s = 0; s < NS; s++) {
         CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
         CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_dec[s], cudaEventDisableTiming));
         CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming));
     }
+    const bool dbg = getenv("CZB_E2E_DEBUG") != nullptr;
+    std::vector<cudaEvent_t> tev;  // debug: 6 timing events per chunk (h2d begin/end, decode begin/end, d2h begin/end)
+    cudaEvent_t t0ev = nullptr;
+    auto tmark = [&](cudaStream_t st) { if (dbg) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    if (dbg) { cudaEventCreate(&t0ev); cudaEventRecord(t0ev, ctx->copy_in); }
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     auto enqueue_in = [&](uint64_t c) -> int {
-        const int s = (int)(c & 1);
+        const int s = (int)(c % NS);
         const uint64_t f0 = cuts[c], f1 = cuts[c + 1], nf = f1 - f0;
-        // slot s is free once chunk c-2's outputs have been copied out
-        if (c >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_out[s], 0));
+        // slot s is free once chunk c-NS's outputs have been copied out
+        if (c >= (uint64_t)NS) CZB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_in, ev_out[s], 0));
         // the aligned base keeps each frame's alignment relative to src_base
         const uint64_t sb = src_off[f0], mis = sb & 15;
+        tmark(ctx->copy_in);
         CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_src[s].p + mis, src_base + sb, src_off[f1] - sb, cudaMemcpyHostToDevice, ctx->copy_in));
+        tmark(ctx->copy_in);
         czb_frame_desc* hd = reinterpret_cast<czb_frame_desc*>(ctx->pin_b) + (uint64_t)s * max_frames;
         const uint64_t db = dst_off[f0], dmis = db & 15;
         for (uint64_t i = 0; i < nf; i++) {
@@ -331,29 +346,48 @@ extern "C" int czb_decode_batch_host_packed(czb_context* ctx, const uint8_t* src
         CZB_CUDA(ctx, cudaEventRecord(ev_in[s], ctx->copy_in));
         return CZS_OK;
     };
+    const double t_begin = now_ms();
     if ((rc = enqueue_in(0))) return rc;
     for (uint64_t c = 0; c < n_chunks; c++) {
-        const int s = (int)(c & 1);
+        const double t_iter = now_ms();
+        const int s = (int)(c % NS);
         const uint64_t f0 = cuts[c], f1 = cuts[c + 1], nf = f1 - f0;
         if (c + 1 < n_chunks) {
-            // pin_b's descriptor half for slot s^1 is reused: its previous H2D (chunk c-1) has completed by now
-            // because chunk c-1's decode (which waited on it) was planned with a stream sync.
+            // pin_b's descriptor part for that slot is reused: its previous H2D (chunk c+1-NS) completed long ago,
+            // because that chunk's decode (which waited on it) was planned with a stream sync.
             if ((rc = enqueue_in(c + 1))) return rc;
         }
         CZB_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ev_in[s], 0));
+        tmark(ctx->compute);
         if ((rc = czb_decode_batch_device(ctx, ctx->h_descs.p + (uint64_t)s * max_frames, ctx->h_results.p + (uint64_t)s * max_frames, nf,
                                           flags, ctx->compute))) return rc;
+        tmark(ctx->compute);
         CZB_CUDA(ctx, cudaEventRecord(ev_dec[s], ctx->compute));
         CZB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_out, ev_dec[s], 0));
         const uint64_t db = dst_off[f0], dmis = db & 15;
+        tmark(ctx->copy_out);
         CZB_CUDA(ctx, cudaMemcpyAsync(dst_base + db, ctx->h_dst[s].p + dmis, dst_off[f1] - db, cudaMemcpyDeviceToHost, ctx->copy_out));
+        tmark(ctx->copy_out);
         CZB_CUDA(ctx, cudaMemcpyAsync(results + f0, ctx->h_results.p + (uint64_t)s * max_frames, nf * sizeof(czb_frame_result),
                                       cudaMemcpyDeviceToHost, ctx->copy_out));
         CZB_CUDA(ctx, cudaEventRecord(ev_out[s], ctx->copy_out));
+        if (dbg) fprintf(stderr, "[e2e] chunk %llu frames %llu: iter start %.1f ms, iter took %.1f ms\n", (unsigned long long)c,
+                         (unsigned long long)nf, t_iter - t_begin, now_ms() - t_iter);
     }
     CZB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_out));
+    if (dbg) {
+        fprintf(stderr, "[e2e] total %.1f ms\n", now_ms() - t_begin);
+        cudaDeviceSynchronize();
+        // event order per chunk c: enqueue_in(c) pushes 2 (h2d), then the loop body pushes 2 (decode) + 2 (d2h);
+        // enqueue_in(c+1) is called before chunk c's decode, so sort by kind using the push pattern.
+        std::vector<float> t(tev.size());
+        for (size_t i = 0; i < tev.size(); i++) cudaEventElapsedTime(&t[i], t0ev, tev[i]);
+        for (size_t i = 0; i + 1 < tev.size(); i += 2) fprintf(stderr, "[e2e-gpu] op %zu: [%.1f, %.1f] ms (%.1f)\n", i / 2, t[i], t[i + 1], t[i + 1] - t[i]);
+        for (auto e : tev) cudaEventDestroy(e);
+        cudaEventDestroy(t0ev);
+    }
     CZB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
-    for (int s = 0; s < 2; s++) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_dec[s]); cudaEventDestroy(ev_out[s]); }
+    for (int s = 0; s < NS; s++) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_dec[s]); cudaEventDestroy(ev_out[s]); }
     return CZS_OK;
 }
 

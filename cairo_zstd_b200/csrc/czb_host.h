@@ -27,7 +27,8 @@ struct czb_context {
     // decode workspace (device)
     DevBuf<czb::FrameInfo> infos;
     DevBuf<czb::WaveTotals> totals_d;
-    czb::WaveTotals* totals_h = nullptr;  // pinned
+    czb::WaveTotals* totals_h = nullptr;      // pinned + mapped
+    czb::WaveTotals* totals_h_dev = nullptr;  // device alias of totals_h
     // per-wave scratch, double-buffered: the entropy stage of wave w+1 overlaps sequence execution of wave w
     DevBuf<czb::WaveCounters> counters[2];
     DevBuf<czb::BlockDesc> blocks[2];
@@ -41,7 +42,8 @@ struct czb_context {
     bool no_overlap = false;
 
     // staging for the host-pointer entry points
-    DevBuf<uint8_t> h_src[2], h_dst[2];
+    static constexpr int kHostSlots = 3;  // staging slots of the packed host path
+    DevBuf<uint8_t> h_src[kHostSlots], h_dst[kHostSlots];
     DevBuf<czb_frame_desc> h_descs;
     DevBuf<czb_frame_result> h_results;
     uint8_t* pin_a = nullptr; uint64_t pin_a_cap = 0;

@@ -216,6 +216,20 @@ __global__ void __launch_bounds__(256) k_header_results(const FrameInfo* __restr
     results[i] = r;
 }
 
+// Copies the per-wave totals into host-mapped memory with plain stores (no copy engine involved).
+__global__ void k_publish_totals(const WaveTotals* __restrict__ src, WaveTotals* __restrict__ dst_host, uint64_t n_waves) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_words = n_waves * (sizeof(WaveTotals) / sizeof(unsigned long long));
+    if (i < n_words) reinterpret_cast<volatile unsigned long long*>(dst_host)[i] = reinterpret_cast<const unsigned long long*>(src)[i];
+    __threadfence_system();
+}
+
+void launch_publish_totals(const LaunchCtx& lc, const WaveTotals* totals_d, WaveTotals* totals_host_mapped, uint64_t n_waves) {
+    const uint64_t n_words = n_waves * (sizeof(WaveTotals) / sizeof(unsigned long long));
+    k_publish_totals<<<(unsigned)((n_words + 127) / 128), 128, 0, lc.stream>>>(totals_d, totals_host_mapped, n_waves);
+    ++*lc.launches;
+}
+
 void launch_scan_frames(const LaunchCtx& lc, const czb_frame_desc* descs, FrameInfo* infos, uint64_t n, uint64_t wave_frames,
                         WaveTotals* totals) {
     if (!n) return;
