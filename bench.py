@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-frames", type=int, default=32768)
+    ap.add_argument("--cpu-sample-frames", type=int, default=131072)
     ap.add_argument("--verify-checksum", action="store_true", help="include the XXH64 kernel in the timed region")
     return ap.parse_args()
 

@@ -23,8 +23,11 @@
 namespace czb {
 
 constexpr int EXEC_WARPS = 4;
+#ifndef EXEC_MIN_CTAS
+#define EXEC_MIN_CTAS 7
+#endif
 #ifndef EXEC_CTAS_PER_SM
-#define EXEC_CTAS_PER_SM 6
+#define EXEC_CTAS_PER_SM 7
 #endif
 constexpr uint32_t EXEC_ROW = 128;
 
@@ -81,7 +84,7 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
     for (uint32_t i = lane; i < n; i += 32) dst[i] = byte;
 }
 
-__global__ void __launch_bounds__(EXEC_WARPS * 32, 6) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
+__global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
                                                            uint64_t count, WaveCounters* __restrict__ counters, BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
