@@ -289,10 +289,15 @@ def run_b200(args, rank, world, local_rank):
                                "frac": alg_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak},
                 "kernel_share_of_step": {k: v[0] / kernel_ms_total for k, v in prof.items()} if kernel_ms_total else {},
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per frame x frames per launch)
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_path):
         try:
-            roofline["traffic"] = json.load(open(traffic_path)).get("k_" + dom_name)
+            tk = json.load(open(traffic_path))["kernels"].get("k_" + dom_name)
+            if tk:
+                roofline["traffic"] = tk["bytes_per_frame"] * n * args.steps / max(dom_launches, 1)
+                roofline["traffic_source"] = "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per frame) x frames per launch"
+                roofline["algorithmic_bytes_per_launch"] = alg_bytes_per_launch
         except Exception:
             pass
 

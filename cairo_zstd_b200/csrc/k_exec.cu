@@ -138,12 +138,13 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
             uint32_t lit_pos = 0;
             __syncwarp();
             const Seq* seqs = seq_scratch + d.seq_off;
-            Seq rec_next = lane < d.n_seq ? seqs[lane] : 0ull;
+            // records are read exactly once: stream them (evict-first) so that L2 keeps the frame's recent output instead
+            Seq rec_next = lane < d.n_seq ? __ldcs(seqs + lane) : 0ull;
             for (uint32_t s0 = 0; s0 < d.n_seq; s0 += 32) {
                 const uint32_t i = s0 + lane;
                 const bool have = i < d.n_seq;
                 const Seq rec = rec_next;
-                if (i + 32 < d.n_seq) rec_next = seqs[i + 32];  // next chunk's record is in flight while this chunk executes
+                if (i + 32 < d.n_seq) rec_next = __ldcs(seqs + i + 32);  // next chunk's record is in flight while this chunk executes
                 uint32_t ll = 0, ml = 0, off = 1;
                 if (have) { ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
                 // warp prefix sums: literal offsets and output offsets (u32 cannot wrap: 32 * (131071 + 131074) < 2^32)

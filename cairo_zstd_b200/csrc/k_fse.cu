@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 h2 = (rep & (idx <= 1)) ? h2 : h1;
                 h1 = (rep & (idx == 0)) ? h1 : h0;
                 h0 = act;
-                out[i] = (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35);
+                __stcs(out + i, (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35));  // written once, read by a later kernel: streaming store
                 if (MORE) {
                     eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
                     eML = tML[(fse_entry_base(eML, nbML, logML) + aML) & mML];
