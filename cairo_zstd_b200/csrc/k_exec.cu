@@ -30,6 +30,10 @@ constexpr int EXEC_WARPS = 4;
 #define EXEC_CTAS_PER_SM 7
 #endif
 constexpr uint32_t EXEC_ROW = 128;
+#ifndef EXEC_TILE_PATH
+#define EXEC_TILE_PATH 1
+#endif
+constexpr uint32_t EXEC_TILE = 1024;
 
 struct ExecWarpSmem {
     uint32_t bound[66];      // bound[2i] = first output byte of sequence i's literal run, [2i+1] = of its match, [64] = span
@@ -37,6 +41,9 @@ struct ExecWarpSmem {
                              // [64] is the "past the end" pseudo segment
     unsigned long long segbase[66];  // indexed by id = segment index + 1: address of the source byte for output position 0
     uint32_t segthr[66];     // indexed by id: a byte at row-relative... see gather: fast iff (p - rlo) < segthr[id]
+#if EXEC_TILE_PATH
+    __align__(16) uint8_t tile[EXEC_TILE + 48];  // a chunk's whole output span (sequence-centric path)
+#endif
     __align__(4) uint8_t rowmap[EXEC_ROW];  // (segment id + 1) at each non-empty segment's start byte inside the row
     __align__(4) uint8_t krow[EXEC_ROW];    // (segment id + 1) owning each row byte
 };
@@ -83,6 +90,80 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
     }
     for (uint32_t i = lane; i < n; i += 32) dst[i] = byte;
 }
+
+#if EXEC_TILE_PATH
+// tile[0..n) = src[0..n), n in 1..16, src in global memory at any alignment: aligned 32-bit loads of only the
+// words that hold needed bytes, one funnel shift per word, then byte stores into shared memory.
+__device__ __forceinline__ void copy16_to_tile(uint8_t* __restrict__ t, const uint8_t* __restrict__ src, uint32_t n) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const uint32_t mis = (uint32_t)(a & 3), sh = mis * 8, need = n + mis;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+    const uint32_t w0 = w[0];
+    const uint32_t w1 = need > 4 ? w[1] : 0u, w2 = need > 8 ? w[2] : 0u, w3 = need > 12 ? w[3] : 0u, w4 = need > 16 ? w[4] : 0u;
+    const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+#pragma unroll
+    for (int k = 0; k < 16; k++) if ((uint32_t)k < n) t[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+}
+
+// Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  Literal runs and
+// matches whose source precedes the chunk are copied 16 bytes at a time (all lanes in parallel, uniform control
+// flow); matches that read this chunk's own output run afterwards in dependency order, byte-serially per lane
+// (which also gives overlapping matches their forward-copy semantics, decode_buffer.cairo:101-120).  The tile is
+// flushed with aligned 16-byte stores.
+__device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* obase, const uint8_t* __restrict__ lits, bool lit_rle,
+                                                uint32_t rle_byte, unsigned lane, uint32_t ll, uint32_t ml, uint32_t off,
+                                                uint32_t my_lit, uint32_t segA, uint32_t span) {
+    const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(obase) & 15);
+    uint8_t* tile = tile_base + a0;  // tile[p] = output byte at chunk-relative position p
+    const uint32_t segM = segA + ll;
+    // literal runs
+    for (uint32_t r = 0; __any_sync(0xFFFFFFFFu, ll > r); r += 16) {
+        if (ll > r) {
+            const uint32_t n = ll - r < 16u ? ll - r : 16u;
+            if (lit_rle) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) if ((uint32_t)k < n) tile[segA + r + k] = (uint8_t)rle_byte;
+            } else copy16_to_tile(tile + segA + r, lits + my_lit + r, n);
+        }
+    }
+    // matches whose whole source precedes the chunk (already in dst)
+    const bool indep = ml > 0 && off >= segM + ml;
+    for (uint32_t r = 0; __any_sync(0xFFFFFFFFu, indep && ml > r); r += 16) {
+        if (indep && ml > r) copy16_to_tile(tile + segM + r, obase + ((int64_t)segM - (int64_t)off) + r, ml - r < 16u ? ml - r : 16u);
+    }
+    __syncwarp();
+    // matches that read this chunk's own output, in dependency order
+    const bool dep = ml > 0 && !indep;
+    unsigned U = __ballot_sync(0xFFFFFFFFu, dep);
+    const int s0 = (int)segM - (int)off, s1 = s0 + (int)ml;  // source range, chunk-relative (may start before the chunk)
+    while (U) {
+        bool ready = (U >> lane) & 1u;
+        for (unsigned m = U; m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const int d0 = __shfl_sync(0xFFFFFFFFu, (int)segM, j), d1 = d0 + __shfl_sync(0xFFFFFFFFu, (int)ml, j);
+            if (j < (int)lane && d0 < s1 && d1 > s0) ready = false;  // an unfinished earlier match still has to write bytes this one reads
+        }
+        const unsigned R = __ballot_sync(0xFFFFFFFFu, ready);
+        for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, ready && k < ml); k++) {
+            if (ready && k < ml) {
+                const int q = s0 + (int)k;
+                tile[segM + k] = q < 0 ? obase[q] : tile[q];
+            }
+        }
+        U &= ~R;
+        __syncwarp();
+    }
+    // flush: aligned 16-byte stores (tile index and dst address agree modulo 16)
+    const uint32_t head = span < ((16 - a0) & 15) ? span : ((16 - a0) & 15);
+    if (lane < head) obase[lane] = tile[lane];
+    const uint32_t body = span - head, nv = body >> 4, tail = body & 15;
+    const uint4* t4 = reinterpret_cast<const uint4*>(tile + head);
+    uint4* g4 = reinterpret_cast<uint4*>(obase + head);
+    for (uint32_t v = lane; v < nv; v += 32) g4[v] = t4[v];
+    if (lane < tail) obase[head + (nv << 4) + lane] = tile[head + (nv << 4) + lane];
+    __syncwarp();
+}
+#endif
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
                                                            uint64_t count, WaveCounters* __restrict__ counters, BlockDesc* __restrict__ blocks,
@@ -169,7 +250,14 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
                 if (errm) { status = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1); break; }
                 const uint32_t span = __shfl_sync(0xFFFFFFFFu, osum, 31);
                 const uint32_t lit_used = __shfl_sync(0xFFFFFFFFu, lsum, 31);
-                // publish the 64 segments of this chunk
+#if EXEC_TILE_PATH
+                if (span <= EXEC_TILE) {  // the common case: short segments, span of a few hundred bytes
+                    exec_chunk_tile(sm.tile, dst + out, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span);
+                    out += span; lit_pos += lit_used;
+                    continue;
+                }
+#endif
+                // general path (long segments): publish the 64 segments of this chunk
                 const uint32_t segA = my_out, segM = my_out + ll;
                 sm.bound[2 * lane] = segA; sm.bound[2 * lane + 1] = segM;
                 sm.segdelta[2 * lane] = (int)my_lit - (int)segA;
