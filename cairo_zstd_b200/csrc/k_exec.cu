@@ -92,23 +92,36 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
 }
 
 #if EXEC_TILE_PATH
-// tile[0..n) = src[0..n), n in 1..16, src in global memory at any alignment: aligned 32-bit loads of only the
-// words that hold needed bytes, one funnel shift per word, then byte stores into shared memory.
-__device__ __forceinline__ void copy16_to_tile(uint8_t* __restrict__ t, const uint8_t* __restrict__ src, uint32_t n) {
+// 16 source bytes starting at src (any alignment, global or shared memory) as four little-endian words.  Only the
+// aligned 32-bit words that hold one of the first n bytes are read.
+struct Vec16 { uint32_t v[4]; };
+__device__ __forceinline__ Vec16 load16_unaligned(const uint8_t* __restrict__ src, uint32_t n) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(src);
     const uint32_t mis = (uint32_t)(a & 3), sh = mis * 8, need = n + mis;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-    const uint32_t w0 = w[0];
+    const uint32_t w0 = n ? w[0] : 0u;
     const uint32_t w1 = need > 4 ? w[1] : 0u, w2 = need > 8 ? w[2] : 0u, w3 = need > 12 ? w[3] : 0u, w4 = need > 16 ? w[4] : 0u;
-    const uint32_t v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+    Vec16 r;
+    r.v[0] = __funnelshift_r(w0, w1, sh); r.v[1] = __funnelshift_r(w1, w2, sh);
+    r.v[2] = __funnelshift_r(w2, w3, sh); r.v[3] = __funnelshift_r(w3, w4, sh);
+    return r;
+}
+// t[0..n) = the first n bytes of x (byte stores into the shared-memory tile).  Groups of four bytes are skipped
+// warp-uniformly when no lane needs them, so short segments do not pay for sixteen predicated stores.
+__device__ __forceinline__ void store16_to_tile(uint8_t* t, const Vec16& x, uint32_t n) {
 #pragma unroll
-    for (int k = 0; k < 16; k++) if ((uint32_t)k < n) t[k] = (uint8_t)(v[k >> 2] >> (8 * (k & 3)));
+    for (int g = 0; g < 4; g++) {
+        if (g == 0 || __any_sync(0xFFFFFFFFu, n > 4u * g)) {
+#pragma unroll
+            for (int k = 4 * g; k < 4 * g + 4; k++) if ((uint32_t)k < n) t[k] = (uint8_t)(x.v[g] >> (8 * (k & 3)));
+        }
+    }
 }
 
-// Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  Literal runs and
-// matches whose source precedes the chunk are copied 16 bytes at a time (all lanes in parallel, uniform control
-// flow); matches that read this chunk's own output run afterwards in dependency order, byte-serially per lane
-// (which also gives overlapping matches their forward-copy semantics, decode_buffer.cairo:101-120).  The tile is
+// Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  Literal runs, matches
+// whose source precedes the chunk, and matches whose source lies in finished parts of the tile are copied 16 bytes
+// at a time (all lanes in parallel, uniform control flow).  Only matches that read another such match's output, or
+// their own (overlapping matches, decode_buffer.cairo:101-120), run byte-serially in dependency order.  The tile is
 // flushed with aligned 16-byte stores.
 __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* obase, const uint8_t* __restrict__ lits, bool lit_rle,
                                                 uint32_t rle_byte, unsigned lane, uint32_t ll, uint32_t ml, uint32_t off,
@@ -116,42 +129,61 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
     const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(obase) & 15);
     uint8_t* tile = tile_base + a0;  // tile[p] = output byte at chunk-relative position p
     const uint32_t segM = segA + ll;
-    // literal runs
-    for (uint32_t r = 0; __any_sync(0xFFFFFFFFu, ll > r); r += 16) {
-        if (ll > r) {
-            const uint32_t n = ll - r < 16u ? ll - r : 16u;
-            if (lit_rle) {
-#pragma unroll
-                for (int k = 0; k < 16; k++) if ((uint32_t)k < n) tile[segA + r + k] = (uint8_t)rle_byte;
-            } else copy16_to_tile(tile + segA + r, lits + my_lit + r, n);
-        }
+    const bool indep = ml > 0 && off >= segM + ml;  // whole source precedes the chunk (already in dst)
+    const uint8_t* msrc = obase + ((int64_t)segM - (int64_t)off);
+    // first 16 bytes of every literal run and independent match: all loads are issued before the stores
+    {
+        const uint32_t nl = lit_rle ? 0u : (ll < 16u ? ll : 16u), nm = indep ? (ml < 16u ? ml : 16u) : 0u;
+        const Vec16 xl = load16_unaligned(lits + my_lit, nl), xm = load16_unaligned(msrc, nm);
+        store16_to_tile(tile + segA, xl, nl);
+        store16_to_tile(tile + segM, xm, nm);
     }
-    // matches whose whole source precedes the chunk (already in dst)
-    const bool indep = ml > 0 && off >= segM + ml;
-    for (uint32_t r = 0; __any_sync(0xFFFFFFFFu, indep && ml > r); r += 16) {
-        if (indep && ml > r) copy16_to_tile(tile + segM + r, obase + ((int64_t)segM - (int64_t)off) + r, ml - r < 16u ? ml - r : 16u);
+    for (uint32_t r = 16; __any_sync(0xFFFFFFFFu, !lit_rle && ll > r); r += 16) {  // long literal runs
+        const uint32_t n = (!lit_rle && ll > r) ? (ll - r < 16u ? ll - r : 16u) : 0u;
+        store16_to_tile(tile + segA + r, load16_unaligned(lits + my_lit + r, n), n);
+    }
+    if (lit_rle) for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, k < ll); k++) if (k < ll) tile[segA + k] = (uint8_t)rle_byte;
+    for (uint32_t r = 16; __any_sync(0xFFFFFFFFu, indep && ml > r); r += 16) {  // long independent matches
+        const uint32_t n = (indep && ml > r) ? (ml - r < 16u ? ml - r : 16u) : 0u;
+        store16_to_tile(tile + segM + r, load16_unaligned(msrc + r, n), n);
     }
     __syncwarp();
-    // matches that read this chunk's own output, in dependency order
+    // matches that read this chunk's own output
     const bool dep = ml > 0 && !indep;
     unsigned U = __ballot_sync(0xFFFFFFFFu, dep);
-    const int s0 = (int)segM - (int)off, s1 = s0 + (int)ml;  // source range, chunk-relative (may start before the chunk)
-    while (U) {
-        bool ready = (U >> lane) & 1u;
+    if (U) {
+        const int s0 = (int)segM - (int)off, s1 = s0 + (int)ml;  // source range, chunk-relative (may start before the chunk)
+        // "clean": the source is entirely inside the tile and touches no dependent match's destination (its own included)
+        bool clean = dep && s0 >= 0 && off >= ml;
         for (unsigned m = U; m; m &= m - 1) {
             const int j = __ffs(m) - 1;
             const int d0 = __shfl_sync(0xFFFFFFFFu, (int)segM, j), d1 = d0 + __shfl_sync(0xFFFFFFFFu, (int)ml, j);
-            if (j < (int)lane && d0 < s1 && d1 > s0) ready = false;  // an unfinished earlier match still has to write bytes this one reads
+            if (d0 < s1 && d1 > s0) clean = false;
         }
-        const unsigned R = __ballot_sync(0xFFFFFFFFu, ready);
-        for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, ready && k < ml); k++) {
-            if (ready && k < ml) {
-                const int q = s0 + (int)k;
-                tile[segM + k] = q < 0 ? obase[q] : tile[q];
-            }
+        for (uint32_t r = 0; __any_sync(0xFFFFFFFFu, clean && ml > r); r += 16) {
+            const uint32_t n = (clean && ml > r) ? (ml - r < 16u ? ml - r : 16u) : 0u;
+            const Vec16 x = load16_unaligned(tile + s0 + r, n);
+            store16_to_tile(tile + segM + r, x, n);
         }
-        U &= ~R;
         __syncwarp();
+        U &= ~__ballot_sync(0xFFFFFFFFu, clean);
+        while (U) {  // the rest, in dependency order, byte-serially per lane
+            bool ready = (U >> lane) & 1u;
+            for (unsigned m = U; m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
+                const int d0 = __shfl_sync(0xFFFFFFFFu, (int)segM, j), d1 = d0 + __shfl_sync(0xFFFFFFFFu, (int)ml, j);
+                if (j < (int)lane && d0 < s1 && d1 > s0) ready = false;  // an unfinished earlier match still has to write bytes this one reads
+            }
+            const unsigned R = __ballot_sync(0xFFFFFFFFu, ready);
+            for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, ready && k < ml); k++) {
+                if (ready && k < ml) {
+                    const int q = s0 + (int)k;
+                    tile[segM + k] = q < 0 ? obase[q] : tile[q];
+                }
+            }
+            U &= ~R;
+            __syncwarp();
+        }
     }
     // flush: aligned 16-byte stores (tile index and dst address agree modulo 16)
     const uint32_t head = span < ((16 - a0) & 15) ? span : ((16 - a0) & 15);
