@@ -8,10 +8,10 @@
 // chain over the same sequences.
 //
 // Mapping: the interleaved LL/OF/ML state machine is one dependency chain per block and cannot be
-// split, so parallelism comes from blocks: a CTA owns 25 blocks, its 4 warps build the 75 tables
+// split, so parallelism comes from blocks: a CTA owns 27 blocks, its 4 warps build the 81 tables
 // cooperatively, then warp 0 decodes with lane = block.  Throughput is bounded by
 // (blocks resident per SM) / (chain latency per sequence); 16-bit table entries (czb_fse_build.cuh)
-// keep a block's three tables at <= 2.5 KiB so 75 blocks fit per SM (three CTAs).  HBM traffic: the
+// keep a block's three tables at <= 2.5 KiB so 81 blocks fit per SM (three CTAs).  HBM traffic: the
 // bitstream in (a few bytes per sequence) and one packed 8-byte record per sequence out to scratch.
 #include <type_traits>
 
@@ -21,8 +21,7 @@
 namespace czb {
 
 constexpr int FSE_WARPS = 4;
-constexpr int FSE_SLOTS = 25;  // 25 * 2560 B of tables + scratch = ~70 KB -> three CTAs (75 decode lanes) per SM, leaving ~17 KB of
-                               // shared memory so k_exec CTAs of the previous wave can co-reside (they use the idle issue slots)
+constexpr int FSE_SLOTS = 27;  // 27 * 2560 B of tables + scratch = ~75 KB -> three CTAs (81 decode lanes) per SM
 constexpr int FSE_SLOT_ENTRIES = 512 + 512 + 256;  // LL (log<=9), ML (log<=9), OF (log<=8)
 constexpr int FSE_LL_OFS = 0, FSE_ML_OFS = 512, FSE_OF_OFS = 1024;
 
@@ -213,11 +212,14 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             Seq* out = sl.out;
             const bool any_rle = sl.any_rle;
             // One sequence (:223-286).  MORE = false is the last sequence: states are not updated (:258).
+            // Both levels of shared-memory lookups are software-pipelined: the next state entries are fetched right
+            // after the bit fields are known (before history, packing and the store), and the code words
+            // (lookup_ll_code / lookup_ml_code) of those entries are fetched at the end of the step for the next one.
+            uint32_t lle = sm.ll_code[fse_entry_sym(eLL)], mle = sm.ml_code[fse_entry_sym(eML)];
             auto step = [&](uint32_t i, auto more_tag) -> bool {
                 constexpr bool MORE = decltype(more_tag)::value;
                 br.topup_if_low();  // avail > 32 from here
-                const uint32_t llc = fse_entry_sym(eLL), mlc = fse_entry_sym(eML), ofc = fse_entry_sym(eOF);
-                const uint32_t lle = sm.ll_code[llc], mle = sm.ml_code[mlc];
+                const uint32_t ofc = fse_entry_sym(eOF);
                 if ((ofc >> 5) | ((lle | mle) >> 31)) {  // :235-237; codes beyond the tables give (0,255) -> TooManyBits
                     st = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
                     return false;
@@ -245,8 +247,13 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                     mlv = br.get_safe((int)mlb); llv = br.get_safe((int)llb);
                     if (MORE) { aLL = br.get_safe((int)nbLL); aML = br.get_safe((int)nbML); aOF = br.get_safe((int)nbOF); }
                 }
-                const uint32_t v = (1u << ofc) + ofv;  // :243
                 const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
+                if (MORE) {  // issue the next-state lookups now; they complete under the history/pack/store work below
+                    eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
+                    eML = tML[(fse_entry_base(eML, nbML, logML) + aML) & mML];
+                    eOF = tOF[(fse_entry_base(eOF, nbOF, logOF) + aOF) & mOF];
+                }
+                const uint32_t v = (1u << ofc) + ofv;  // :243
                 // do_offset_history (sequence_execution.cairo:85-129) with selects only:
                 // idx 0,1,2 = history slot, 3 = h0 - 1 (reachable only when ll == 0)
                 const uint32_t idx = v - (ll != 0);
@@ -261,11 +268,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 h1 = (rep & (idx == 0)) ? h1 : h0;
                 h0 = act;
                 __stcs(out + i, (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35));  // written once, read by a later kernel: streaming store
-                if (MORE) {
-                    eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
-                    eML = tML[(fse_entry_base(eML, nbML, logML) + aML) & mML];
-                    eOF = tOF[(fse_entry_base(eOF, nbOF, logOF) + aOF) & mOF];
-                }
+                if (MORE) { lle = sm.ll_code[fse_entry_sym(eLL)]; mle = sm.ml_code[fse_entry_sym(eML)]; }
                 if (br.rem < 0) {  // :281-283; the no-RLE variant traps on the unwrap at :279 instead
                     st = any_rle ? CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES : CZS_PANIC_INTERNAL;
                     return false;
