@@ -80,7 +80,7 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p);
     for (int s = 0; s < 2; s++) {
-        cudaFree(ctx->huf_cls0[s].p); cudaFree(ctx->huf_cls1[s].p); cudaFree(ctx->huf_recs[s].p);
+        cudaFree(ctx->exec_order[s].p); cudaFree(ctx->huf_cls0[s].p); cudaFree(ctx->huf_cls1[s].p); cudaFree(ctx->huf_recs[s].p);
         cudaFree(ctx->blocks[s].p); cudaFree(ctx->huf_items[s].p); cudaFree(ctx->fse_items[s].p); cudaFree(ctx->lit[s].p);
         cudaFree(ctx->seq[s].p); cudaFree(ctx->counters[s].p);
         if (ctx->ev_entropy[s]) cudaEventDestroy(ctx->ev_entropy[s]);
@@ -153,7 +153,9 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
     uint64_t W = std::min<uint64_t>((n + 127) / 128 * 128, ctx->wave_frames);
     while ((n + W - 1) / W > kMaxWaves) W *= 2;
     uint64_t n_waves = 0;
+    bool exact_classes = true;  // per-section size classes come from the scan; a planning retry only has per-frame data
     for (int attempt = 0;; attempt++) {
+        exact_classes = attempt == 0;
         n_waves = (n + W - 1) / W;
         if (attempt == 0) {
             CZB_CUDA(ctx, cudaMemsetAsync(ctx->totals_d.p, 0, n_waves * sizeof(WaveTotals), stream));
@@ -180,6 +182,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         if ((rc = ensure(ctx, ctx->counters[s], 1))) return rc;
         if ((rc = ensure(ctx, ctx->blocks[s], mx.n_blocks + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_items[s], mx.n_huf + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->exec_order[s], W + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_cls0[s], mx.n_huf + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_cls1[s], mx.n_huf + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_recs[s], mx.n_huf + 1))) return rc;
@@ -203,16 +206,18 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         const int s = overlap ? (int)(w & 1) : 0;
         const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
         const WaveTotals& t = ctx->totals_h[w];
+        uint32_t n_exec = 0;
+        for (int c = 0; c < 32; c++) n_exec += t.frame_cls[c];
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
-        { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p); }
+        { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0); }
         { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p, ctx->huf_recs[s].p, ctx->huf_cls0[s].p, ctx->huf_cls1[s].p); }
         { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks[s].p, ctx->fse_items[s].p, ctx->counters[s].p, (uint32_t)t.n_fse, ctx->seq[s].p); }
         if (overlap) {
             CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
-        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, ctx->counters[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, n_exec, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;

@@ -32,7 +32,7 @@ struct czb_context {
     // per-wave scratch, double-buffered: the entropy stage of wave w+1 overlaps sequence execution of wave w
     DevBuf<czb::WaveCounters> counters[2];
     DevBuf<czb::BlockDesc> blocks[2];
-    DevBuf<uint32_t> huf_items[2], fse_items[2], huf_cls0[2], huf_cls1[2];
+    DevBuf<uint32_t> huf_items[2], fse_items[2], huf_cls0[2], huf_cls1[2], exec_order[2];
     DevBuf<czb::HufRec> huf_recs[2];
     DevBuf<uint8_t> lit[2];
     DevBuf<czb::Seq> seq[2];

@@ -198,7 +198,8 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
 #endif
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
-                                                           uint64_t count, WaveCounters* __restrict__ counters, BlockDesc* __restrict__ blocks,
+                                                           uint64_t count, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
+                                                           BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
     __shared__ ExecWarpSmem smem[EXEC_WARPS];
@@ -209,8 +210,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
     for (;;) {
     unsigned int fq = 0;
     if (lane == 0) fq = atomicAdd(&counters->exec_next, 1u);
-    const uint64_t f = __shfl_sync(0xFFFFFFFFu, fq, 0);
-    if (f >= count) break;
+    const uint64_t qpos = __shfl_sync(0xFFFFFFFFu, fq, 0);
+    if (qpos >= n_exec) break;
+    const uint64_t f = exec_order[qpos];  // largest frames first
     const FrameInfo fi = infos[f];
     if (fi.status != CZS_OK) continue;  // k_header_results already reported it
     const czb_frame_desc fd = descs[f];
@@ -431,12 +433,12 @@ static int exec_persistent_ctas() {
     return n;
 }
 
-void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count,
-                 WaveCounters* counters, BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
-    if (!count) return;
-    const uint64_t want = (count + EXEC_WARPS - 1) / EXEC_WARPS;
+void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_exec,
+                 WaveCounters* counters, const uint32_t* exec_order, BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
+    if (!count || !n_exec) return;
+    const uint64_t want = ((uint64_t)n_exec + EXEC_WARPS - 1) / EXEC_WARPS;
     const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
-    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, counters, blocks, lit_scratch, seq_scratch, results + first);
+    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
     ++*lc.launches;
 }
 

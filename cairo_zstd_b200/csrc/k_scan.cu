@@ -46,6 +46,9 @@ __device__ __forceinline__ uint64_t align16(uint64_t v) { return (v + 15) & ~15u
 
 __global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __restrict__ descs, FrameInfo* __restrict__ infos,
                                                       uint64_t n, uint64_t wave_frames, WaveTotals* __restrict__ totals) {
+    __shared__ unsigned int hist[2][32];
+    if (threadIdx.x < 64) hist[threadIdx.x >> 5][threadIdx.x & 31] = 0;
+    __syncthreads();
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     FrameInfo fi;
     memset(&fi, 0, sizeof fi);
@@ -84,6 +87,10 @@ __global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __res
                 }
             }
             src_bytes = pos;
+            fi.size_cls = size_class(pos);
+            fi.fse_cls = fi.n_fse ? size_class(fi.n_seq / fi.n_fse) : 0u;
+            atomicAdd(&hist[0][fi.size_cls], 1u);
+            if (fi.n_fse) atomicAdd(&hist[1][fi.fse_cls], fi.n_fse);
         }
         infos[i] = fi;
     }
@@ -98,6 +105,13 @@ __global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __res
         if (nh) atomicAdd(&t->n_huf, nh);
         if (nf) atomicAdd(&t->n_fse, nf);
         if (sb) atomicAdd(&t->src_bytes, sb);
+    }
+    // size-class histograms: one global atomic per class per CTA (a CTA never straddles waves)
+    __syncthreads();
+    if (threadIdx.x < 64 && (uint64_t)blockIdx.x * blockDim.x < n) {
+        const unsigned int c = hist[threadIdx.x >> 5][threadIdx.x & 31];
+        WaveTotals* t = totals + ((uint64_t)blockIdx.x * blockDim.x) / wave_frames;
+        if (c) atomicAdd((threadIdx.x >> 5) ? &t->fse_cls[threadIdx.x & 31] : &t->frame_cls[threadIdx.x & 31], c);
     }
 }
 
@@ -116,6 +130,32 @@ __global__ void __launch_bounds__(128) k_wave_totals(const FrameInfo* __restrict
         if (nh) atomicAdd(&t->n_huf, nh);
         if (nf) atomicAdd(&t->n_fse, nf);
     }
+    // size classes for the new wave split (same per-frame classes as the scan)
+    if (i < n && infos[i].status == CZS_OK) {
+        const FrameInfo& fi = infos[i];
+        WaveTotals* t = totals + i / wave_frames;
+        atomicAdd(&t->frame_cls[fi.size_cls & 31u], 1u);
+        if (fi.n_fse) atomicAdd(&t->fse_cls[fi.fse_cls & 31u], fi.n_fse);
+    }
+}
+
+// Reserve n units in the per-class counter of class `cls` for this lane; lanes of a warp that share a class get
+// one atomic and consecutive ranges in lane order, so neighbouring frames stay neighbours in the work lists
+// (k_fse's 27 lanes then read neighbouring bitstreams: same DRAM pages, same TLB entries).
+__device__ __forceinline__ unsigned int warp_reserve_by_class(unsigned int* counters, uint32_t cls, unsigned int n) {
+    const unsigned lane = lane_id();
+    unsigned int before = 0, total = 0;
+    int leader = -1;
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) {
+        const uint32_t cj = __shfl_sync(0xFFFFFFFFu, cls, j);
+        const unsigned int nj = __shfl_sync(0xFFFFFFFFu, n, j);
+        if (cj == cls) { if (leader < 0) leader = j; total += nj; if (j < (int)lane) before += nj; }
+    }
+    unsigned int base = 0;
+    if ((int)lane == leader && total) base = atomicAdd(&counters[cls & 31u], total);
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + before;
 }
 
 // Second walk: write one BlockDesc per block, resolve the table-reuse chains
@@ -124,7 +164,15 @@ __global__ void __launch_bounds__(128) k_wave_totals(const FrameInfo* __restrict
 __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __restrict__ descs, FrameInfo* __restrict__ infos,
                                                       uint64_t first, uint64_t count, BlockDesc* __restrict__ blocks,
                                                       uint32_t* __restrict__ huf_items, uint32_t* __restrict__ fse_items,
-                                                      WaveCounters* __restrict__ ctr) {
+                                                      WaveCounters* __restrict__ ctr, const WaveTotals* __restrict__ wt,
+                                                      uint32_t* __restrict__ exec_order, int exact_fse_classes) {
+    // start of every size class in the work lists, largest class first
+    __shared__ unsigned int frame_start[32], fse_start[32];
+    if (threadIdx.x == 0) {
+        unsigned int a = 0, b = 0;
+        for (int c = 31; c >= 0; c--) { frame_start[c] = a; a += wt->frame_cls[c]; fse_start[c] = b; b += wt->fse_cls[c]; }
+    }
+    __syncthreads();
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = t < count;
     const uint64_t i = first + (active ? t : 0);
@@ -136,9 +184,16 @@ __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __res
     unsigned long long seq_base = warp_reserve<unsigned long long>(&ctr->n_seq, walk ? fi.n_seq : 0);
     unsigned int huf_base = warp_reserve<unsigned int>(&ctr->n_huf, walk ? fi.n_huf : 0);
     unsigned int fse_base = warp_reserve<unsigned int>(&ctr->n_fse, walk ? fi.n_fse : 0);
+    (void)fse_base;
+    // positions in the size-ordered work lists (inactive lanes get private dummy classes with nothing to reserve)
+    const uint32_t fcls = walk ? (fi.size_cls & 31u) : 64u + lane_id(), scls = (walk && fi.n_fse) ? (fi.fse_cls & 31u) : 64u + lane_id();
+    const unsigned int frame_pos = warp_reserve_by_class(ctr->frame_fill, fcls, walk ? 1u : 0u);
+    unsigned int fse_pos = warp_reserve_by_class(ctr->fse_fill, scls, (walk && fi.n_fse) ? fi.n_fse : 0u);
     if (!active) return;
     infos[i].block_base = (uint32_t)blk_base;
     if (!walk) return;
+    exec_order[frame_start[fi.size_cls & 31u] + frame_pos] = (uint32_t)(i - first);  // k_exec takes the biggest size class first
+    fse_pos += fse_start[fi.fse_cls & 31u];
 
     const uint8_t* src = descs[i].src;
     uint64_t len = descs[i].src_len;
@@ -192,7 +247,7 @@ __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __res
                         d.first_in_frame = seen_seq ? 0 : 1;
                         seen_seq = true;
                         d.seq_off = seq_base; seq_base += pb.n_seq;
-                        fse_items[fse_base++] = bidx;
+                        fse_items[fse_pos++] = bidx;
                     }
                 }
             }
@@ -244,9 +299,11 @@ void launch_wave_totals(const LaunchCtx& lc, const FrameInfo* infos, uint64_t n,
     ++*lc.launches;
 }
 void launch_fill_blocks(const LaunchCtx& lc, const czb_frame_desc* descs, FrameInfo* infos, uint64_t first, uint64_t count,
-                        BlockDesc* blocks, uint32_t* huf_items, uint32_t* fse_items, WaveCounters* counters) {
+                        BlockDesc* blocks, uint32_t* huf_items, uint32_t* fse_items, WaveCounters* counters,
+                        const WaveTotals* wave_totals, uint32_t* exec_order, int exact_fse_classes) {
     if (!count) return;
-    k_fill_blocks<<<(unsigned)((count + 127) / 128), 128, 0, lc.stream>>>(descs, infos, first, count, blocks, huf_items, fse_items, counters);
+    k_fill_blocks<<<(unsigned)((count + 127) / 128), 128, 0, lc.stream>>>(descs, infos, first, count, blocks, huf_items, fse_items, counters,
+                                                                          wave_totals, exec_order, exact_fse_classes);
     ++*lc.launches;
 }
 void launch_header_results(const LaunchCtx& lc, const FrameInfo* infos, czb_frame_result* results, uint64_t n) {
