@@ -28,16 +28,20 @@ __device__ __forceinline__ uint32_t fse_entry_nbits(uint32_t e, uint32_t log) { 
 __device__ __forceinline__ uint32_t fse_entry_base(uint32_t e, uint32_t nb, uint32_t log) { return ((e & 1023u) << nb) - (1u << log); }
 
 // Serial (one lane).  probs[] receives up to FSE_MAX_SYMBOLS entries; n_probs counts all of them.
-// unsupported_log: set when log passes max_log (the reference's check) but exceeds FSE_MAX_LOG.
+// A description whose accuracy log passes max_log (the reference's check) but exceeds FSE_MAX_LOG -- only possible
+// for Huffman weights, where the reference passes 100 (huff0_decoder.cairo:176) -- is still parsed to the end so
+// that every error the reference would raise is raised; if it parses cleanly CZS_UNSUPPORTED is returned with
+// bytes_read set (the caller may still prefer its own "used too many bytes" error).
 __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int max_log, int16_t* probs, int& n_probs, int& log,
                                                  int& bytes_read) {
     FwdBits br{p, len, 0};
     uint32_t v;
     n_probs = 0;
+    bytes_read = 0;
     if (!br.get(4, v)) return CZS_FSE_GET_BITS_ERROR;
     log = 5 + (int)v;
     if (log > max_log) return CZS_FSE_ACC_LOG_TOO_BIG;
-    if (log > FSE_MAX_LOG) return CZS_UNSUPPORTED;  // only reachable for Huffman weights (max_log = 100, huff0_decoder.cairo:176)
+    const bool oversize = log > FSE_MAX_LOG;
     const uint32_t sum = 1u << log;
     uint32_t counter = 0;
     while (counter < sum) {
@@ -53,7 +57,7 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
         else if (unchecked > mask) value = unchecked - low_threshold;
         else value = unchecked;
         const int prob = (int)value - 1;
-        if (n_probs < FSE_MAX_SYMBOLS) probs[n_probs] = (int16_t)prob;
+        if (n_probs < FSE_MAX_SYMBOLS && !oversize) probs[n_probs] = (int16_t)prob;
         n_probs++;
         if (prob != 0) {
             counter += prob > 0 ? (uint32_t)prob : 1u;
@@ -61,7 +65,7 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
             for (;;) {
                 uint32_t skip;
                 if (!br.get(2, skip)) return CZS_FSE_GET_BITS_ERROR;
-                for (uint32_t k = 0; k < skip; k++) { if (n_probs < FSE_MAX_SYMBOLS) probs[n_probs] = 0; n_probs++; }
+                for (uint32_t k = 0; k < skip; k++) { if (n_probs < FSE_MAX_SYMBOLS && !oversize) probs[n_probs] = 0; n_probs++; }
                 if (skip != 3) break;
             }
         }
@@ -69,7 +73,7 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
     if (counter != sum) return CZS_FSE_PROBABILITY_COUNTER_MISMATCH;
     if (n_probs > 256) return CZS_FSE_TOO_MANY_SYMBOLS;
     bytes_read = (br.idx + 7) >> 3;
-    return CZS_OK;
+    return oversize ? CZS_UNSUPPORTED : CZS_OK;
 }
 
 // Warp-cooperative table build.  probs[0..n) in shared memory (modified: becomes the running

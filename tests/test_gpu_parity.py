@@ -110,6 +110,19 @@ def test_direct_weight_headers_follow_rfc_order():
     assert all(a == b for a, b in zip(outs, origs))
 
 
+def test_huffman_streams_with_non_rfc_split_decode_like_the_reference():
+    """The reference concatenates the four streams and checks only the total
+    (literals_section_decoder.cairo:203-240), so any split that sums to regenerated_size decodes."""
+    import handmade as H
+    splits = [[[0, 1], [1, 1], [0, 0], [1, 0]], [[0, 1, 1], [1], [0, 0], [1, 0]],
+              [[0, 1, 1, 1, 0, 1, 1, 0, 0, 1, 0], [1], [0], [1, 0, 1]], [[0, 1], [1, 1], [0, 0], [1, 0, 1]],
+              [[1] * 40, [0] * 3, [1, 0] * 9, [0]]]
+    built = [H.huf4_two_symbol_frame(s) for s in splits]
+    outs, res = compare_with_oracle([f for f, _ in built], [64] * len(built), label="non-rfc-split")
+    assert all(r.status == 0 for r in res)
+    assert outs == [e for _, e in built]
+
+
 def test_empty_and_tiny_frames(corpus):
     cz = W.Compressor()
     origs = [b"", b"a", b"ab" * 3, b"\x00" * 70000, bytes(range(256)) * 3]

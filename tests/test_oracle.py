@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from cairo_zstd_b200 import workloads as W
+from cairo_zstd_b200 import api, workloads as W
 
 
 # --------------------------------------------------------------------------
@@ -296,3 +296,16 @@ def test_incremental_surface_upto_blocks(corpus):
     L.oracle_fd_getters(fd, C.byref(r))
     assert r.blocks_decoded == res_full.blocks_decoded and r.checksum_calculated == r.checksum_from_data
     L.oracle_fd_free(fd)
+
+
+def test_handmade_huffman_split_frames_decode():
+    """Frames assembled by tests/handmade.py: the oracle, like the reference, accepts any four-stream split whose
+    total is regenerated_size (literals_section_decoder.cairo:203-240)."""
+    import handmade as H
+    for streams in ([[0, 1], [1, 1], [0, 0], [1, 0]], [[0, 1, 1], [1], [0, 0], [1, 0]], [[0, 1], [1, 1], [0, 0], [1, 0, 1]]):
+        f, e = H.huf4_two_symbol_frame(streams)
+        st, out, _ = O.decode_frame(f, dst_cap=64)
+        assert st == 0 and out == e
+    f, _ = H.huf4_two_symbol_frame([[0, 1], [1, 1], [0, 0], [1, 0]])
+    b = bytearray(f); b[9] += 0x10  # literals header says 9 regenerated bytes, the streams hold 8
+    assert O.decode_frame(bytes(b), dst_cap=64)[0] == {v: k for k, v in api.STATUS_NAMES.items()}["CZS_DECODED_LITERAL_COUNT_MISMATCH"]
