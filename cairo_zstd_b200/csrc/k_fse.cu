@@ -20,6 +20,9 @@
 
 namespace czb {
 
+#ifndef CZB_FSE_RING
+#define CZB_FSE_RING 1  // sequence bitstream through per-lane cp.async rings (RevBitsRing) instead of register-pipelined words (RevBits)
+#endif
 constexpr int FSE_WARPS = 4;
 constexpr int FSE_SLOTS = 27;  // 27 * 2560 B of tables + scratch = ~75 KB -> three CTAs (81 decode lanes) per SM
 constexpr int FSE_SLOT_ENTRIES = 512 + 512 + 256;  // LL (log<=9), ML (log<=9), OF (log<=8)
@@ -38,10 +41,11 @@ struct FseSlot {
     uint8_t any_rle;
 };
 
-struct FseWarpTmp {
+struct alignas(16) FseWarpTmp {
     int16_t probs[FSE_MAX_SYMBOLS];
     uint8_t rank_sym[1 << FSE_MAX_LOG];
 };
+static_assert(sizeof(FseWarpTmp) * FSE_WARPS >= FSE_SLOTS * RevBitsRing::RING, "phase-2 rings reuse phase-1 scratch");
 
 struct FseSmem {
     uint16_t entries[FSE_SLOTS * FSE_SLOT_ENTRIES + 64 + 32 + 64];  // per-slot tables, then predefined LL, OF, ML
@@ -195,8 +199,15 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
     if (sl.first_in_frame) { h0 = 1; h1 = 4; h2 = 8; }  // scratch.cairo:35
     else { h0 = sym_enc(0); h1 = sym_enc(1); h2 = sym_enc(2); }
     if (st == CZS_OK) {
+#if CZB_FSE_RING
+        // phase 1's scratch is dead now (the other warps have left): it becomes the lanes' bitstream rings
+        RevBitsRing br;
+        const bool init_ok = br.init(sl.bits, (int)sl.bits_len, (uint32_t)__cvta_generic_to_shared(sm.tmp) + lane * RevBitsRing::RING);
+#else
         RevBits br;
-        if (!br.init(sl.bits, (int)sl.bits_len)) st = CZS_SEQ_EXTRA_PADDING;  // :46-64
+        const bool init_ok = br.init(sl.bits, (int)sl.bits_len);
+#endif
+        if (!init_ok) st = CZS_SEQ_EXTRA_PADDING;  // :46-64
         else if (sl.log[0] < 0 || sl.log[1] < 0 || sl.log[2] < 0) st = CZS_FSE_TABLE_IS_UNINITIALIZED;  // fse_decoder.cairo:82-84
         else {
             const uint32_t logLL = (uint32_t)sl.log[0], logOF = (uint32_t)sl.log[1], logML = (uint32_t)sl.log[2];
@@ -218,6 +229,9 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             uint32_t lle = sm.ll_code[fse_entry_sym(eLL)], mle = sm.ml_code[fse_entry_sym(eML)];
             auto step = [&](uint32_t i, auto more_tag) -> bool {
                 constexpr bool MORE = decltype(more_tag)::value;
+#if CZB_FSE_RING
+                br.step_sync();
+#endif
                 br.topup_if_low();  // avail > 32 from here
                 const uint32_t ofc = fse_entry_sym(eOF);
                 if ((ofc >> 5) | ((lle | mle) >> 31)) {  // :235-237; codes beyond the tables give (0,255) -> TooManyBits
