@@ -118,6 +118,14 @@ __device__ __forceinline__ void store16_to_tile(uint8_t* t, const Vec16& x, uint
     }
 }
 
+// All lanes copy n bytes src -> tile + dst_off for the lane `j` that owns the job (arguments are taken from lane j).
+__device__ __forceinline__ void coop_copy_to_tile(uint8_t* tile, unsigned lane, int j, uint32_t dst_off, const uint8_t* src, uint32_t n) {
+    const uint32_t d = __shfl_sync(0xFFFFFFFFu, dst_off, j), cnt = __shfl_sync(0xFFFFFFFFu, n, j);
+    const unsigned long long sp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uintptr_t>(src), j);
+    const uint8_t* s = reinterpret_cast<const uint8_t*>((uintptr_t)sp);
+    for (uint32_t i = lane; i < cnt; i += 32) tile[d + i] = s[i];
+}
+
 // Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  Literal runs, matches
 // whose source precedes the chunk, and matches whose source lies in finished parts of the tile are copied 16 bytes
 // at a time (all lanes in parallel, uniform control flow).  Only matches that read another such match's output, or
@@ -138,15 +146,13 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
         store16_to_tile(tile + segA, xl, nl);
         store16_to_tile(tile + segM, xm, nm);
     }
-    for (uint32_t r = 16; __any_sync(0xFFFFFFFFu, !lit_rle && ll > r); r += 16) {  // long literal runs
-        const uint32_t n = (!lit_rle && ll > r) ? (ll - r < 16u ? ll - r : 16u) : 0u;
-        store16_to_tile(tile + segA + r, load16_unaligned(lits + my_lit + r, n), n);
-    }
+    // Tails beyond the first 16 bytes are rare (a few per cent of the segments) and may be long: the whole warp
+    // copies each one instead of every lane looping in lockstep for the longest.
+    for (unsigned m = __ballot_sync(0xFFFFFFFFu, !lit_rle && ll > 16u); m; m &= m - 1)
+        coop_copy_to_tile(tile, lane, __ffs(m) - 1, segA + 16u, lits + my_lit + 16, ll - 16u);
     if (lit_rle) for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, k < ll); k++) if (k < ll) tile[segA + k] = (uint8_t)rle_byte;
-    for (uint32_t r = 16; __any_sync(0xFFFFFFFFu, indep && ml > r); r += 16) {  // long independent matches
-        const uint32_t n = (indep && ml > r) ? (ml - r < 16u ? ml - r : 16u) : 0u;
-        store16_to_tile(tile + segM + r, load16_unaligned(msrc + r, n), n);
-    }
+    for (unsigned m = __ballot_sync(0xFFFFFFFFu, indep && ml > 16u); m; m &= m - 1)
+        coop_copy_to_tile(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
     __syncwarp();
     // matches that read this chunk's own output
     const bool dep = ml > 0 && !indep;

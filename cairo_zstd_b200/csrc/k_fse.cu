@@ -24,7 +24,10 @@ namespace czb {
 #define CZB_FSE_RING 1  // sequence bitstream through per-lane cp.async rings (RevBitsRing) instead of register-pipelined words (RevBits)
 #endif
 constexpr int FSE_WARPS = 4;
-constexpr int FSE_SLOTS = 27;  // 27 * 2560 B of tables + scratch = ~75 KB -> three CTAs (81 decode lanes) per SM
+#ifndef CZB_FSE_SLOTS
+#define CZB_FSE_SLOTS 27
+#endif
+constexpr int FSE_SLOTS = CZB_FSE_SLOTS;  // 27 * 2560 B of tables + scratch = ~75 KB -> three CTAs (81 decode lanes) per SM
 constexpr int FSE_SLOT_ENTRIES = 512 + 512 + 256;  // LL (log<=9), ML (log<=9), OF (log<=8)
 constexpr int FSE_LL_OFS = 0, FSE_ML_OFS = 512, FSE_OF_OFS = 1024;
 
