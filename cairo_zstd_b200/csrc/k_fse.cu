@@ -20,9 +20,6 @@
 
 namespace czb {
 
-#ifndef CZB_FSE_RING
-#define CZB_FSE_RING 1  // sequence bitstream through per-lane cp.async rings (RevBitsRing) instead of register-pipelined words (RevBits)
-#endif
 constexpr int FSE_WARPS = 4;
 #ifndef CZB_FSE_SLOTS
 #define CZB_FSE_SLOTS 27
@@ -202,14 +199,9 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
     if (sl.first_in_frame) { h0 = 1; h1 = 4; h2 = 8; }  // scratch.cairo:35
     else { h0 = sym_enc(0); h1 = sym_enc(1); h2 = sym_enc(2); }
     if (st == CZS_OK) {
-#if CZB_FSE_RING
         // phase 1's scratch is dead now (the other warps have left): it becomes the lanes' bitstream rings
-        RevBitsRing br;
-        const bool init_ok = br.init(sl.bits, (int)sl.bits_len, (uint32_t)__cvta_generic_to_shared(sm.tmp) + lane * RevBitsRing::RING);
-#else
-        RevBits br;
-        const bool init_ok = br.init(sl.bits, (int)sl.bits_len);
-#endif
+        RevBitsWin br;
+        const bool init_ok = br.init(sl.bits, (int)sl.bits_len, (uint32_t)__cvta_generic_to_shared(sm.tmp) + lane * RevBitsWin::RING);
         if (!init_ok) st = CZS_SEQ_EXTRA_PADDING;  // :46-64
         else if (sl.log[0] < 0 || sl.log[1] < 0 || sl.log[2] < 0) st = CZS_FSE_TABLE_IS_UNINITIALIZED;  // fse_decoder.cairo:82-84
         else {
@@ -218,59 +210,62 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             const uint16_t* tLL = sm.entries + sl.tbl[0];
             const uint16_t* tOF = sm.entries + sl.tbl[1];
             const uint16_t* tML = sm.entries + sl.tbl[2];
-            // init order LL, OF, ML (:207-218): at most 26 bits, the reader holds more than 32
+            // init order LL, OF, ML (:207-218)
             uint32_t eLL = tLL[br.get((int)logLL)];
             uint32_t eOF = tOF[br.get((int)logOF)];
             uint32_t eML = tML[br.get((int)logML)];
             const uint32_t n_seq = sl.n_seq;
             Seq* out = sl.out;
-            const bool any_rle = sl.any_rle;
+            const int32_t short_status = sl.any_rle ? CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES : CZS_PANIC_INTERNAL;
             // One sequence (:223-286).  MORE = false is the last sequence: states are not updated (:258).
-            // Both levels of shared-memory lookups are software-pipelined: the next state entries are fetched right
-            // after the bit fields are known (before history, packing and the store), and the code words
-            // (lookup_ll_code / lookup_ml_code) of those entries are fetched at the end of the step for the next one.
+            //
+            // The lane runs alone on its scheduler most of the time, so a step costs the sum of its issue stalls.
+            // Hence: (a) all lookups are software-pipelined -- the next states, their num_bits, their code words
+            // (lookup_ll_code / lookup_ml_code) and the next 32 stream bits are requested as soon as their inputs
+            // exist and consumed one step later; (b) no data-dependent branches -- errors are recorded (first one
+            // wins) and the loop runs on, which is safe because table indices are masked, records stay inside
+            // this block's slice of the scratch and ring reads wrap; the ring refill is a predicated cp.async.
             uint32_t lle = sm.ll_code[fse_entry_sym(eLL)], mle = sm.ml_code[fse_entry_sym(eML)];
-            auto step = [&](uint32_t i, auto more_tag) -> bool {
+            uint32_t win = br.window();
+            uint32_t nbLL = fse_entry_nbits(eLL, logLL), nbML = fse_entry_nbits(eML, logML), nbOF = fse_entry_nbits(eOF, logOF);
+            auto step = [&](uint32_t i, auto more_tag) {
                 constexpr bool MORE = decltype(more_tag)::value;
-#if CZB_FSE_RING
                 br.step_sync();
-#endif
-                br.topup_if_low();  // avail > 32 from here
                 const uint32_t ofc = fse_entry_sym(eOF);
-                if ((ofc >> 5) | ((lle | mle) >> 31)) {  // :235-237; codes beyond the tables give (0,255) -> TooManyBits
-                    st = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
-                    return false;
-                }
-                const uint32_t llb = lle >> 20, mlb = mle >> 20;
-                uint32_t nbLL = 0, nbML = 0, nbOF = 0;
-                if (MORE) { nbLL = fse_entry_nbits(eLL, logLL); nbML = fse_entry_nbits(eML, logML); nbOF = fse_entry_nbits(eOF, logOF); }
-                const uint32_t total = ofc + mlb + llb + nbLL + nbML + nbOF;
+                // :235-237; codes beyond the tables give (0,255) -> TooManyBits
+                const bool bad_code = ((ofc >> 5) | ((lle | mle) >> 31)) != 0;
+                const int32_t code_status = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
+                st = (st == CZS_OK && bad_code) ? code_status : st;
+                const uint32_t llb = (lle >> 20) & 31u, mlb = (mle >> 20) & 31u, ofb = ofc & 31u;
+                if (!MORE) { nbLL = 0; nbML = 0; nbOF = 0; }
+                const uint32_t total = ofb + mlb + llb + nbLL + nbML + nbOF;
                 uint32_t ofv, mlv, llv, aLL = 0, aML = 0, aOF = 0;
                 if (total <= 32) {
-                    // every field comes out of the top 32 bits: read order OF, ML, LL (:239) then LL, ML, OF (:258-276).
+                    // every field comes out of the 32-bit window: read order OF, ML, LL (:239) then LL, ML, OF (:258-276).
                     // PTX shl/shr clamp the shift amount, so zero-width fields read as 0.
-                    uint32_t x = (uint32_t)(br.buf >> 32);
+                    uint32_t x = win;
                     auto take = [&x](uint32_t n) -> uint32_t {
                         uint32_t v, sh = 32u - n;
                         asm("shr.b32 %0, %1, %2;" : "=r"(v) : "r"(x), "r"(sh));
                         asm("shl.b32 %0, %1, %2;" : "=r"(x) : "r"(x), "r"(n));
                         return v;
                     };
-                    ofv = take(ofc); mlv = take(mlb); llv = take(llb);
+                    ofv = take(ofb); mlv = take(mlb); llv = take(llb);
                     if (MORE) { aLL = take(nbLL); aML = take(nbML); aOF = take(nbOF); }
-                    br.skip((int)total);
+                    br.P -= (int)total;
+                    br.refill();
                 } else {  // rare: long offsets with long extra bits
-                    ofv = br.get((int)ofc);
-                    mlv = br.get_safe((int)mlb); llv = br.get_safe((int)llb);
-                    if (MORE) { aLL = br.get_safe((int)nbLL); aML = br.get_safe((int)nbML); aOF = br.get_safe((int)nbOF); }
+                    ofv = br.get((int)ofb); mlv = br.get((int)mlb); llv = br.get((int)llb);
+                    if (MORE) { aLL = br.get((int)nbLL); aML = br.get((int)nbML); aOF = br.get((int)nbOF); }
                 }
+                if (MORE) win = br.window();  // the next step's bits: two LDS issued next to the state lookups below
                 const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
                 if (MORE) {  // issue the next-state lookups now; they complete under the history/pack/store work below
                     eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
                     eML = tML[(fse_entry_base(eML, nbML, logML) + aML) & mML];
                     eOF = tOF[(fse_entry_base(eOF, nbOF, logOF) + aOF) & mOF];
                 }
-                const uint32_t v = (1u << ofc) + ofv;  // :243
+                const uint32_t v = (1u << ofb) + ofv;  // :243
                 // do_offset_history (sequence_execution.cairo:85-129) with selects only:
                 // idx 0,1,2 = history slot, 3 = h0 - 1 (reachable only when ll == 0)
                 const uint32_t idx = v - (ll != 0);
@@ -285,18 +280,18 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 h1 = (rep & (idx == 0)) ? h1 : h0;
                 h0 = act;
                 __stcs(out + i, (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35));  // written once, read by a later kernel: streaming store
-                if (MORE) { lle = sm.ll_code[fse_entry_sym(eLL)]; mle = sm.ml_code[fse_entry_sym(eML)]; }
-                if (br.rem < 0) {  // :281-283; the no-RLE variant traps on the unwrap at :279 instead
-                    st = any_rle ? CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES : CZS_PANIC_INTERNAL;
-                    return false;
+                if (MORE) {
+                    lle = sm.ll_code[fse_entry_sym(eLL)]; mle = sm.ml_code[fse_entry_sym(eML)];
+                    nbLL = fse_entry_nbits(eLL, logLL); nbML = fse_entry_nbits(eML, logML); nbOF = fse_entry_nbits(eOF, logOF);
                 }
-                return true;
+                // :281-283; the no-RLE variant traps on the unwrap at :279 instead
+                st = (st == CZS_OK && br.rem() < 0) ? short_status : st;
             };
-            bool ok = true;
             uint32_t i = 0;
-            for (; ok && i + 1 < n_seq; i++) ok = step(i, std::true_type{});
-            if (ok) step(i, std::false_type{});
-            if (st == CZS_OK && br.rem > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
+#pragma unroll 2
+            for (; i + 1 < n_seq; i++) step(i, std::true_type{});
+            step(i, std::false_type{});
+            if (st == CZS_OK && br.rem() > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
         }
     }
     BlockDesc& d = blocks[sl.blk];
