@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             // wins) and the loop runs on, which is safe because table indices are masked, records stay inside
             // this block's slice of the scratch and ring reads wrap; the ring refill is a predicated cp.async.
             uint32_t lle = sm.ll_code[fse_entry_sym(eLL)], mle = sm.ml_code[fse_entry_sym(eML)];
-            uint32_t win = br.window();
+            RevBitsWin::Raw win = br.window_raw();
             uint32_t nbLL = fse_entry_nbits(eLL, logLL), nbML = fse_entry_nbits(eML, logML), nbOF = fse_entry_nbits(eOF, logOF);
             auto step = [&](uint32_t i, auto more_tag) {
                 constexpr bool MORE = decltype(more_tag)::value;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 if (total <= 32) {
                     // every field comes out of the 32-bit window: read order OF, ML, LL (:239) then LL, ML, OF (:258-276).
                     // PTX shl/shr clamp the shift amount, so zero-width fields read as 0.
-                    uint32_t x = win;
+                    uint32_t x = RevBitsWin::window_of(win);
                     auto take = [&x](uint32_t n) -> uint32_t {
                         uint32_t v, sh = 32u - n;
                         asm("shr.b32 %0, %1, %2;" : "=r"(v) : "r"(x), "r"(sh));
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                     ofv = br.get((int)ofb); mlv = br.get((int)mlb); llv = br.get((int)llb);
                     if (MORE) { aLL = br.get((int)nbLL); aML = br.get((int)nbML); aOF = br.get((int)nbOF); }
                 }
-                if (MORE) win = br.window();  // the next step's bits: two LDS issued next to the state lookups below
+                if (MORE) win = br.window_raw();  // the next step's bits: two LDS issued next to the state lookups below
                 const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
                 if (MORE) {  // issue the next-state lookups now; they complete under the history/pack/store work below
                     eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 st = (st == CZS_OK && br.rem() < 0) ? short_status : st;
             };
             uint32_t i = 0;
-#pragma unroll 2
+#pragma unroll 4
             for (; i + 1 < n_seq; i++) step(i, std::true_type{});
             step(i, std::false_type{});
             if (st == CZS_OK && br.rem() > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
