@@ -45,7 +45,7 @@ struct alignas(16) FseWarpTmp {
     int16_t probs[FSE_MAX_SYMBOLS];
     uint8_t rank_sym[1 << FSE_MAX_LOG];
 };
-static_assert(sizeof(FseWarpTmp) * FSE_WARPS >= FSE_SLOTS * RevBitsRing::RING, "phase-2 rings reuse phase-1 scratch");
+static_assert(sizeof(FseWarpTmp) * FSE_WARPS >= FSE_SLOTS * (RevBitsWin::RING + 16), "phase-2 rings (+ one 16-byte dummy slot per lane) reuse phase-1 scratch");
 
 struct FseSmem {
     uint16_t entries[FSE_SLOTS * FSE_SLOT_ENTRIES + 64 + 32 + 64];  // per-slot tables, then predefined LL, OF, ML
@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             // wins) and the loop runs on, which is safe because table indices are masked, records stay inside
             // this block's slice of the scratch and ring reads wrap; the ring refill is a predicated cp.async.
             uint32_t lle = sm.ll_code[fse_entry_sym(eLL)], mle = sm.ml_code[fse_entry_sym(eML)];
-            RevBitsWin::Raw win = br.window_raw();
+            RevBitsWin::Raw64 win = br.window64_raw();
+            const uint32_t dummy = (uint32_t)__cvta_generic_to_shared(sm.tmp) + FSE_SLOTS * RevBitsWin::RING + lane * 16u;
             uint32_t nbLL = fse_entry_nbits(eLL, logLL), nbML = fse_entry_nbits(eML, logML), nbOF = fse_entry_nbits(eOF, logOF);
             auto step = [&](uint32_t i, auto more_tag) {
                 constexpr bool MORE = decltype(more_tag)::value;
@@ -237,28 +238,25 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 const int32_t code_status = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
                 st = (st == CZS_OK && bad_code) ? code_status : st;
                 const uint32_t llb = (lle >> 20) & 31u, mlb = (mle >> 20) & 31u, ofb = ofc & 31u;
-                if (!MORE) { nbLL = 0; nbML = 0; nbOF = 0; }
-                const uint32_t total = ofb + mlb + llb + nbLL + nbML + nbOF;
-                uint32_t ofv, mlv, llv, aLL = 0, aML = 0, aOF = 0;
-                if (total <= 32) {
-                    // every field comes out of the 32-bit window: read order OF, ML, LL (:239) then LL, ML, OF (:258-276).
-                    // PTX shl/shr clamp the shift amount, so zero-width fields read as 0.
-                    uint32_t x = RevBitsWin::window_of(win);
-                    auto take = [&x](uint32_t n) -> uint32_t {
-                        uint32_t v, sh = 32u - n;
-                        asm("shr.b32 %0, %1, %2;" : "=r"(v) : "r"(x), "r"(sh));
-                        asm("shl.b32 %0, %1, %2;" : "=r"(x) : "r"(x), "r"(n));
-                        return v;
-                    };
-                    ofv = take(ofb); mlv = take(mlb); llv = take(llb);
-                    if (MORE) { aLL = take(nbLL); aML = take(nbML); aOF = take(nbOF); }
-                    br.P -= (int)total;
-                    br.refill();
-                } else {  // rare: long offsets with long extra bits
-                    ofv = br.get((int)ofb); mlv = br.get((int)mlb); llv = br.get((int)llb);
-                    if (MORE) { aLL = br.get((int)nbLL); aML = br.get((int)nbML); aOF = br.get((int)nbOF); }
+                const uint32_t extras = ofb + mlb + llb;  // <= 63 bits, read in the order OF, ML, LL (:239)
+                // The three state updates (LL, ML, OF, <= 26 bits, :258-276) come from their own 32-bit window below the
+                // extra bits, whose position is known from the start of the step: no "does it all fit in 32 bits" branch.
+                RevBitsWin::Raw winB;
+                if (MORE) winB = br.window_raw_at(br.P - (int)extras);
+                const uint32_t xh = __funnelshift_r(win.w1, win.w2, win.sh), xl = __funnelshift_r(win.w0, win.w1, win.sh);
+                const uint32_t ofv = shr_clamp(xh, 32u - ofb);
+                const uint32_t y = __funnelshift_l(xl, xh, ofb);
+                const uint32_t mlv = shr_clamp(y, 32u - mlb), llv = shr_clamp(y << mlb, 32u - llb);
+                uint32_t aLL = 0, aML = 0, aOF = 0;
+                if (MORE) {
+                    const uint32_t z = RevBitsWin::window_of(winB);
+                    aLL = shr_clamp(z, 32u - nbLL); aML = shr_clamp(z << nbLL, 32u - nbML); aOF = shr_clamp(z << (nbLL + nbML), 32u - nbOF);
+                    br.P -= (int)(extras + nbLL + nbML + nbOF);
+                    br.refill_nobranch(dummy);
+                    win = br.window64_raw();  // the next step's bits: three LDS issued next to the state lookups below
+                } else {
+                    br.P -= (int)extras;
                 }
-                if (MORE) win = br.window_raw();  // the next step's bits: two LDS issued next to the state lookups below
                 const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
                 if (MORE) {  // issue the next-state lookups now; they complete under the history/pack/store work below
                     eLL = tLL[(fse_entry_base(eLL, nbLL, logLL) + aLL) & mLL];
