@@ -123,6 +123,40 @@ def test_huffman_streams_with_non_rfc_split_decode_like_the_reference():
     assert outs == [e for _, e in built]
 
 
+def test_small_workspace_budget_splits_into_many_waves():
+    """A 24 MB workspace forces the planner to shrink waves far below the batch; results must not depend on it."""
+    frames, origs = W.config2_text_frames(24, 65536)
+    frames, origs = frames * 30, origs * 30  # 720 frames, ~47 MB of output
+    small = czb.Context(0, 24 << 20)
+    outs, res = small.decode_batch(frames, [len(o) for o in origs], api.FLAG_VERIFY_CHECKSUM)
+    assert all(r.status == 0 and r.checksum_calculated == r.checksum_from_data for r in res)
+    assert outs == origs
+
+
+def test_packed_host_path_chunks_and_error_frames(monkeypatch):
+    """czb_decode_batch_host_packed (the e2e path of bench.py): several staging chunks, one broken frame in the middle."""
+    import ctypes as C
+    monkeypatch.setenv("CZB_HOST_CHUNK_MB", "4")
+    frames, origs = W.config2_text_frames(32, 65536)
+    frames, origs = list(frames) * 8, list(origs) * 8  # 256 frames, 16 MB out: several 4 MB chunks
+    bad = len(frames) // 2
+    frames[bad] = frames[bad][: len(frames[bad]) // 2]
+    n = len(frames)
+    src = np.frombuffer(b"".join(frames), dtype=np.uint8).copy()
+    src_off = np.zeros(n + 1, dtype=np.uint64); src_off[1:] = np.cumsum([len(f) for f in frames])
+    dst_off = np.zeros(n + 1, dtype=np.uint64); dst_off[1:] = np.cumsum([len(o) for o in origs])
+    dst = np.zeros(int(dst_off[-1]), dtype=np.uint8)
+    results = (api.FrameResult * n)()
+    packed = czb.Context(0)
+    packed.decode_batch_packed(src.ctypes.data, src_off, dst.ctypes.data, dst_off, n, C.addressof(results), api.FLAG_VERIFY_CHECKSUM)
+    for k in range(n):
+        if k == bad:
+            assert results[k].status == O.decode_frame(frames[k], dst_cap=len(origs[k]))[0] != 0
+            continue
+        assert results[k].status == 0 and results[k].bytes_written == len(origs[k])
+        assert dst[int(dst_off[k]):int(dst_off[k + 1])].tobytes() == origs[k], k
+
+
 def test_empty_and_tiny_frames(corpus):
     cz = W.Compressor()
     origs = [b"", b"a", b"ab" * 3, b"\x00" * 70000, bytes(range(256)) * 3]
