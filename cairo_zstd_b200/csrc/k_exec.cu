@@ -30,6 +30,9 @@ constexpr int EXEC_WARPS = 4;
 #define EXEC_CTAS_PER_SM 7
 #endif
 constexpr uint32_t EXEC_ROW = 128;
+#ifndef EXEC_DEP_COOP
+#define EXEC_DEP_COOP 1  // in-chunk dependent matches: whole warp per match in order (0: per-lane clean/ready analysis)
+#endif
 #ifndef EXEC_TILE_PATH
 #define EXEC_TILE_PATH 1
 #endif
@@ -154,6 +157,22 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
     for (unsigned m = __ballot_sync(0xFFFFFFFFu, indep && ml > 16u); m; m &= m - 1)
         coop_copy_to_tile(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
     __syncwarp();
+#if EXEC_DEP_COOP
+    // Matches that read this chunk's own output (a few per chunk): in sequence order, the whole warp on each one, so
+    // every source byte is final when it is read.  A match that overlaps itself (offset < length,
+    // decode_buffer.cairo:101-120) repeats its first `offset` source bytes, which lie before its destination.
+    for (unsigned U = __ballot_sync(0xFFFFFFFFu, ml > 0 && !indep); U; U &= U - 1) {
+        const int j = __ffs(U) - 1;
+        const uint32_t dM = __shfl_sync(0xFFFFFFFFu, segM, j), n = __shfl_sync(0xFFFFFFFFu, ml, j), o = __shfl_sync(0xFFFFFFFFu, off, j);
+        const int s0 = (int)dM - (int)o;  // chunk-relative source start, may lie before the chunk (already in dst)
+        if (o >= n) {
+            for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)i; tile[dM + i] = q < 0 ? obase[q] : tile[q]; }
+        } else {
+            for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)(i % o); tile[dM + i] = q < 0 ? obase[q] : tile[q]; }
+        }
+        __syncwarp();
+    }
+#else
     // matches that read this chunk's own output
     const bool dep = ml > 0 && !indep;
     unsigned U = __ballot_sync(0xFFFFFFFFu, dep);
@@ -191,6 +210,7 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
             __syncwarp();
         }
     }
+#endif
     // flush: aligned 16-byte stores (tile index and dst address agree modulo 16)
     const uint32_t head = span < ((16 - a0) & 15) ? span : ((16 - a0) & 15);
     if (lane < head) obase[lane] = tile[lane];
