@@ -297,19 +297,26 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
                 }
                 const uint32_t my_lit = lit_pos + lsum - ll;      // literals_copy_counter before this sequence
                 const uint32_t my_out = osum - ll - ml;           // output offset of the literal run, relative to chunk base
-                const uint64_t before_match = out + my_out + ll;  // DecodeBuffer.len() when repeat() is called
-                int32_t err = CZS_OK;
-                if (have) {
-                    if (ll > 0 && (uint64_t)my_lit + ll > n_lit) err = CZS_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE;  // :29-37
-                    else if (off == 0) err = CZS_EXEC_ZERO_OFFSET;                                            // :47-49
-                    else if (ml > 0 && off > before_match)                                                      // decode_buffer.cairo:65-93
-                        err = (before_match <= fi.window) ? CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY : CZS_OFFSET_TOO_BIG;
-                    else if (before_match + ml > cap) err = cap_status;
-                }
-                const unsigned errm = __ballot_sync(0xFFFFFFFFu, err != CZS_OK);
-                if (errm) { status = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1); break; }
                 const uint32_t span = __shfl_sync(0xFFFFFFFFu, osum, 31);
                 const uint32_t lit_used = __shfl_sync(0xFFFFFFFFu, lsum, 31);
+                // Errors are rare: one cheap test that is exact for "some lane fails" (totals for the literal and
+                // capacity checks, one unsigned compare per lane for offset 0 / offset beyond the output so far;
+                // out <= cap < 2^28, so 32 bits suffice), then the reference's checks in its order only if it fires.
+                const uint32_t before_match32 = (uint32_t)out + my_out + ll;
+                const bool suspicious = (uint64_t)lit_pos + lit_used > n_lit || out + span > cap || (have && off - 1u >= before_match32);
+                if (__any_sync(0xFFFFFFFFu, suspicious)) {
+                    const uint64_t before_match = out + my_out + ll;  // DecodeBuffer.len() when repeat() is called
+                    int32_t err = CZS_OK;
+                    if (have) {
+                        if (ll > 0 && (uint64_t)my_lit + ll > n_lit) err = CZS_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE;  // :29-37
+                        else if (off == 0) err = CZS_EXEC_ZERO_OFFSET;                                            // :47-49
+                        else if (ml > 0 && off > before_match)                                                      // decode_buffer.cairo:65-93
+                            err = (before_match <= fi.window) ? CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY : CZS_OFFSET_TOO_BIG;
+                        else if (before_match + ml > cap) err = cap_status;
+                    }
+                    const unsigned errm = __ballot_sync(0xFFFFFFFFu, err != CZS_OK);
+                    if (errm) { status = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1); break; }
+                }
 #if EXEC_TILE_PATH
                 if (span <= EXEC_TILE) {  // the common case: short segments, span of a few hundred bytes
                     exec_chunk_tile(sm.tile, dst + out, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span);
