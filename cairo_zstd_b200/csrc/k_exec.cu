@@ -129,6 +129,12 @@ __device__ __forceinline__ void coop_copy_to_tile(uint8_t* tile, unsigned lane, 
     for (uint32_t i = lane; i < cnt; i += 32) tile[d + i] = s[i];
 }
 
+// the same without the votes
+__device__ __forceinline__ void store16_to_tile_all(uint8_t* t, const Vec16& x, uint32_t n) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) if ((uint32_t)k < n) t[k] = (uint8_t)(x.v[k >> 2] >> (8 * (k & 3)));
+}
+
 // Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  Literal runs, matches
 // whose source precedes the chunk, and matches whose source lies in finished parts of the tile are copied 16 bytes
 // at a time (all lanes in parallel, uniform control flow).  Only matches that read another such match's output, or
@@ -146,8 +152,8 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
     {
         const uint32_t nl = lit_rle ? 0u : (ll < 16u ? ll : 16u), nm = indep ? (ml < 16u ? ml : 16u) : 0u;
         const Vec16 xl = load16_unaligned(lits + my_lit, nl), xm = load16_unaligned(msrc, nm);
-        store16_to_tile(tile + segA, xl, nl);
-        store16_to_tile(tile + segM, xm, nm);
+        store16_to_tile(tile + segA, xl, nl);      // literal runs average under three bytes: later groups are usually skipped
+        store16_to_tile_all(tile + segM, xm, nm);  // matches average nine: some lane always needs every group, votes only cost
     }
     // Tails beyond the first 16 bytes are rare (a few per cent of the segments) and may be long: the whole warp
     // copies each one instead of every lane looping in lockstep for the longest.
