@@ -30,9 +30,6 @@ constexpr int EXEC_WARPS = 4;
 #define EXEC_CTAS_PER_SM 7
 #endif
 constexpr uint32_t EXEC_ROW = 128;
-#ifndef EXEC_DEP_COOP
-#define EXEC_DEP_COOP 1  // in-chunk dependent matches: whole warp per match in order (0: per-lane clean/ready analysis)
-#endif
 #ifndef EXEC_TILE_PATH
 #define EXEC_TILE_PATH 1
 #endif
@@ -163,7 +160,6 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
     for (unsigned m = __ballot_sync(0xFFFFFFFFu, indep && ml > 16u); m; m &= m - 1)
         coop_copy_to_tile(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
     __syncwarp();
-#if EXEC_DEP_COOP
     // Matches that read this chunk's own output (a few per chunk): in sequence order, the whole warp on each one, so
     // every source byte is final when it is read.  A match that overlaps itself (offset < length,
     // decode_buffer.cairo:101-120) repeats its first `offset` source bytes, which lie before its destination.
@@ -178,45 +174,6 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
         }
         __syncwarp();
     }
-#else
-    // matches that read this chunk's own output
-    const bool dep = ml > 0 && !indep;
-    unsigned U = __ballot_sync(0xFFFFFFFFu, dep);
-    if (U) {
-        const int s0 = (int)segM - (int)off, s1 = s0 + (int)ml;  // source range, chunk-relative (may start before the chunk)
-        // "clean": the source is entirely inside the tile and touches no dependent match's destination (its own included)
-        bool clean = dep && s0 >= 0 && off >= ml;
-        for (unsigned m = U; m; m &= m - 1) {
-            const int j = __ffs(m) - 1;
-            const int d0 = __shfl_sync(0xFFFFFFFFu, (int)segM, j), d1 = d0 + __shfl_sync(0xFFFFFFFFu, (int)ml, j);
-            if (d0 < s1 && d1 > s0) clean = false;
-        }
-        for (uint32_t r = 0; __any_sync(0xFFFFFFFFu, clean && ml > r); r += 16) {
-            const uint32_t n = (clean && ml > r) ? (ml - r < 16u ? ml - r : 16u) : 0u;
-            const Vec16 x = load16_unaligned(tile + s0 + r, n);
-            store16_to_tile(tile + segM + r, x, n);
-        }
-        __syncwarp();
-        U &= ~__ballot_sync(0xFFFFFFFFu, clean);
-        while (U) {  // the rest, in dependency order, byte-serially per lane
-            bool ready = (U >> lane) & 1u;
-            for (unsigned m = U; m; m &= m - 1) {
-                const int j = __ffs(m) - 1;
-                const int d0 = __shfl_sync(0xFFFFFFFFu, (int)segM, j), d1 = d0 + __shfl_sync(0xFFFFFFFFu, (int)ml, j);
-                if (j < (int)lane && d0 < s1 && d1 > s0) ready = false;  // an unfinished earlier match still has to write bytes this one reads
-            }
-            const unsigned R = __ballot_sync(0xFFFFFFFFu, ready);
-            for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, ready && k < ml); k++) {
-                if (ready && k < ml) {
-                    const int q = s0 + (int)k;
-                    tile[segM + k] = q < 0 ? obase[q] : tile[q];
-                }
-            }
-            U &= ~R;
-            __syncwarp();
-        }
-    }
-#endif
     // flush: aligned 16-byte stores (tile index and dst address agree modulo 16)
     const uint32_t head = span < ((16 - a0) & 15) ? span : ((16 - a0) & 15);
     if (lane < head) obase[lane] = tile[lane];
