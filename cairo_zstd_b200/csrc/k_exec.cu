@@ -6,18 +6,20 @@
 // DecodeBuffer::push / repeat (src/decoding/decode_buffer.cairo:57-133) and collect() (:224-231):
 // the append-only RingBuffer (ring_buffer.cairo:6) is simply the caller's dst span.
 //
-// Mapping: sequences are taken 32 at a time (lane = sequence).  A warp prefix sum over
-// literal/match lengths gives every sequence its literal source and output offsets; each of the
-// 64 segments (literal run / match per sequence) publishes its start and a source delta in shared
-// memory.  The chunk's output span is then produced OUTPUT-CENTRICALLY in rows of 128 bytes that are
-// 4-byte aligned in dst: lane l owns the aligned word at row + 4l.  Segment ownership of every row
-// byte comes from one warp max-scan over "segment id at its start byte" marks; each byte is then a
-// single gather (literal buffer or earlier output at p + delta) and the word is stored with one
-// coalesced 32-bit store.  Control flow is uniform across lanes.  Only bytes whose source lies
-// inside the row being built, overlapping matches (decode_buffer.cairo:101-120) and RLE literals
-// take a per-byte path that chases the source back through the row's segment map.
-// HBM traffic per frame: literals + 8 B/sequence in, decoded bytes out; match sources are recent
-// output and mostly hit L1/L2.
+// Mapping: sequences are taken 32 at a time (lane = sequence).  A warp prefix sum over literal/match lengths gives
+// every sequence its literal source and output offsets.
+//   * Tile path (the chunk's output span fits 1 KiB, the common case): the first 16 bytes of every literal run and of
+//     every match whose source precedes the chunk go into a shared-memory tile with per-lane unaligned 16-byte copies;
+//     everything sparse -- tails beyond 16 bytes, matches that read the chunk's own output (in sequence order,
+//     overlapping ones as a repeated pattern, decode_buffer.cairo:101-120) -- is done by the whole warp, one item at
+//     a time; the tile is flushed with aligned 16-byte stores.
+//   * Row path (longer spans): each of the 64 segments publishes its start and a source delta in shared memory; output
+//     is produced in rows of 128 bytes, lane l owns the aligned word at row + 4l; segment ownership of every row byte
+//     comes from one warp max-scan over "segment id at its start byte" marks; each byte is one gather; bytes whose
+//     source lies inside the row being built, overlapping matches and RLE literals chase the source back through
+//     the row's segment map.
+// HBM traffic per frame: literals + 8 B/sequence in, decoded bytes out; match sources are recent output (L1/L2 when the
+// in-flight working set allows, DRAM otherwise: profiles/r01_final_ncu_summary.md).
 #include "czb_internal.cuh"
 
 namespace czb {
@@ -167,7 +169,9 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
         const int j = __ffs(U) - 1;
         const uint32_t dM = __shfl_sync(0xFFFFFFFFu, segM, j), n = __shfl_sync(0xFFFFFFFFu, ml, j), o = __shfl_sync(0xFFFFFFFFu, off, j);
         const int s0 = (int)dM - (int)o;  // chunk-relative source start, may lie before the chunk (already in dst)
-        if (o >= n) {
+        if (o >= n && s0 >= 0) {  // the usual case: source inside the tile, no self-overlap
+            for (uint32_t i = lane; i < n; i += 32) tile[dM + i] = tile[(uint32_t)s0 + i];
+        } else if (o >= n) {
             for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)i; tile[dM + i] = q < 0 ? obase[q] : tile[q]; }
         } else {
             for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)(i % o); tile[dM + i] = q < 0 ? obase[q] : tile[q]; }

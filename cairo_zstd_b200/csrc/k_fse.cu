@@ -10,9 +10,10 @@
 // Mapping: the interleaved LL/OF/ML state machine is one dependency chain per block and cannot be
 // split, so parallelism comes from blocks: a CTA owns 27 blocks, its 4 warps build the 81 tables
 // cooperatively, then warp 0 decodes with lane = block.  Throughput is bounded by
-// (blocks resident per SM) / (chain latency per sequence); 16-bit table entries (czb_fse_build.cuh)
-// keep a block's three tables at <= 2.5 KiB so 81 blocks fit per SM (three CTAs).  HBM traffic: the
-// bitstream in (a few bytes per sequence) and one packed 8-byte record per sequence out to scratch.
+// (blocks resident per SM) / (cycles per sequence step of a warp that is alone on its scheduler);
+// 16-bit table entries (czb_fse_build.cuh) keep a block's three tables at <= 2.5 KiB so 81 blocks
+// fit per SM (three CTAs).  HBM traffic: the bitstream in (a few bytes per sequence, through
+// per-lane cp.async rings) and one packed 8-byte record per sequence out to scratch.
 #include <type_traits>
 
 #include "czb_fse_build.cuh"
