@@ -15,6 +15,7 @@
 namespace czb {
 int setup_huff_attributes();
 int setup_fse_attributes();
+int setup_exec_attributes();
 }  // namespace czb
 
 using namespace czb;
@@ -56,7 +57,11 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     ctx->no_overlap = getenv("CZB_OVERLAP") == nullptr;
     if (const char* e = getenv("CZB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (uint64_t)atoll(e) << 20;  // measurement aid: run every kernel alone
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
-    if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0) { delete ctx; return CZS_CUDA_ERROR; }
+    if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0 || setup_exec_attributes() != 0) { delete ctx; return CZS_CUDA_ERROR; }
+    // frames whose compressed size is at least 2^big_cls bytes get a whole CTA in sequence execution (k_exec_big)
+    // and whose sequences are sparse (at least big_seq_bytes compressed bytes per sequence; 0 = any).  Knobs for tests.
+    if (const char* e = getenv("CZB_BIG_CLS")) ctx->big_cls = atoi(e);
+    if (const char* e = getenv("CZB_BIG_SEQ_BYTES")) ctx->big_seq_bytes = atoi(e);
     // Planning read-back buffer: host memory mapped into the device address space.  A kernel writes the
     // per-wave totals straight into it, so the read-back never queues behind a large device-to-host
     // copy on the copy engine (that serialised decode behind the previous chunk's output transfer).
@@ -206,8 +211,8 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         const int s = overlap ? (int)(w & 1) : 0;
         const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
         const WaveTotals& t = ctx->totals_h[w];
-        uint32_t n_exec = 0;
-        for (int c = 0; c < 32; c++) n_exec += t.frame_cls[c];
+        uint32_t n_exec = 0, n_big = 0;
+        for (int c = 0; c < 32; c++) { n_exec += t.frame_cls[c]; if (c >= ctx->big_cls) n_big += t.frame_cls[c]; }
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
         { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0); }
@@ -217,7 +222,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
             CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
-        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, n_exec, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, n_big, n_exec, (uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;

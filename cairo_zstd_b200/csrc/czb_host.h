@@ -40,6 +40,8 @@ struct czb_context {
     cudaEvent_t ev_entropy[2] = {nullptr, nullptr}, ev_exec[2] = {nullptr, nullptr}, ev_fork = nullptr;
     int last_set = 0;
     bool no_overlap = false;
+    int big_cls = 19;           // frames of >= 2^big_cls compressed bytes are executed by one CTA each (k_exec_big); 32 = never
+    int big_seq_bytes = 16;     // ... if they have at least this many compressed bytes per sequence (sparse sequences)
 
     // staging for the host-pointer entry points
     static constexpr int kHostSlots = 3;  // staging slots of the packed host path

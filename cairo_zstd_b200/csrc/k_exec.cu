@@ -134,18 +134,31 @@ __device__ __forceinline__ void store16_to_tile_all(uint8_t* t, const Vec16& x, 
     for (int k = 0; k < 16; k++) if ((uint32_t)k < n) t[k] = (uint8_t)(x.v[k >> 2] >> (8 * (k & 3)));
 }
 
-// Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  Literal runs, matches
-// whose source precedes the chunk, and matches whose source lies in finished parts of the tile are copied 16 bytes
-// at a time (all lanes in parallel, uniform control flow).  Only matches that read another such match's output, or
-// their own (overlapping matches, decode_buffer.cairo:101-120), run byte-serially in dependency order.  The tile is
-// flushed with aligned 16-byte stores.
+// Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  The first 16 bytes of
+// every literal run and of every match whose source is already in dst are copied by their own lane (all lanes in
+// parallel, uniform control flow); tails and the matches that depend on output not yet in dst are done by the whole
+// warp, one at a time, in sequence order.  The tile is flushed with aligned 16-byte stores.
+//
+// avail_rel (<= 0) and wait_prev exist for k_exec_big, where several warps work on consecutive chunks of one frame:
+// output below obase + avail_rel is complete in dst when the call starts; wait_prev() returns once everything
+// below obase is.  The one-warp-per-frame kernel passes 0 and a no-op.
+// Which frames get a whole CTA (k_exec_big) instead of one warp (k_exec).  Large ones whose sequences are sparse:
+// with dense short matches nearly every chunk reads the output of the chunks just before it, the in-order commit
+// chain then serialises the warps and one warp per frame is faster (measured: text frames of 1..4 MiB 115 vs 54 GB/s,
+// long-window frames 12 vs 8 GB/s; literal-heavy 1 MiB frames 253 vs 365 GB/s the other way round).
+__device__ __forceinline__ bool frame_is_big(const FrameInfo& fi, uint32_t big_cls, uint32_t big_seq_bytes) {
+    return fi.size_cls >= big_cls && fi.n_seq * big_seq_bytes <= fi.src_end;
+}
+
+struct NoWait { __device__ __forceinline__ void operator()() const {} };
+template <bool CG_LOADS, typename WaitPrev>
 __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* obase, const uint8_t* __restrict__ lits, bool lit_rle,
                                                 uint32_t rle_byte, unsigned lane, uint32_t ll, uint32_t ml, uint32_t off,
-                                                uint32_t my_lit, uint32_t segA, uint32_t span) {
+                                                uint32_t my_lit, uint32_t segA, uint32_t span, int avail_rel, WaitPrev wait_prev) {
     const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(obase) & 15);
     uint8_t* tile = tile_base + a0;  // tile[p] = output byte at chunk-relative position p
     const uint32_t segM = segA + ll;
-    const bool indep = ml > 0 && off >= segM + ml;  // whole source precedes the chunk (already in dst)
+    const bool indep = ml > 0 && (int)(segM + ml) - (int)off <= avail_rel;  // whole source is already in dst
     const uint8_t* msrc = obase + ((int64_t)segM - (int64_t)off);
     // first 16 bytes of every literal run and independent match: all loads are issued before the stores
     {
@@ -162,6 +175,7 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
     for (unsigned m = __ballot_sync(0xFFFFFFFFu, indep && ml > 16u); m; m &= m - 1)
         coop_copy_to_tile(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
     __syncwarp();
+    wait_prev();
     // Matches that read this chunk's own output (a few per chunk): in sequence order, the whole warp on each one, so
     // every source byte is final when it is read.  A match that overlaps itself (offset < length,
     // decode_buffer.cairo:101-120) repeats its first `offset` source bytes, which lie before its destination.
@@ -172,9 +186,9 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
         if (o >= n && s0 >= 0) {  // the usual case: source inside the tile, no self-overlap
             for (uint32_t i = lane; i < n; i += 32) tile[dM + i] = tile[(uint32_t)s0 + i];
         } else if (o >= n) {
-            for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)i; tile[dM + i] = q < 0 ? obase[q] : tile[q]; }
+            for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)i; tile[dM + i] = q < 0 ? (CG_LOADS ? __ldcg(obase + q) : obase[q]) : tile[q]; }
         } else {
-            for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)(i % o); tile[dM + i] = q < 0 ? obase[q] : tile[q]; }
+            for (uint32_t i = lane; i < n; i += 32) { const int q = s0 + (int)(i % o); tile[dM + i] = q < 0 ? (CG_LOADS ? __ldcg(obase + q) : obase[q]) : tile[q]; }
         }
         __syncwarp();
     }
@@ -191,7 +205,7 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
 #endif
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
-                                                           uint64_t count, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
+                                                           uint64_t count, uint32_t big_cls, uint32_t big_seq_bytes, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
                                                            BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
@@ -208,6 +222,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
     const uint64_t f = exec_order[qpos];  // largest frames first
     const FrameInfo fi = infos[f];
     if (fi.status != CZS_OK) continue;  // k_header_results already reported it
+    if (frame_is_big(fi, big_cls, big_seq_bytes)) continue;  // k_exec_big's
     const czb_frame_desc fd = descs[f];
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
                 }
 #if EXEC_TILE_PATH
                 if (span <= EXEC_TILE) {  // the common case: short segments, span of a few hundred bytes
-                    exec_chunk_tile(sm.tile, dst + out, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span);
+                    exec_chunk_tile<false>(sm.tile, dst + out, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span, 0, NoWait{});
                     out += span; lit_pos += lit_used;
                     continue;
                 }
@@ -422,6 +437,235 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
     }  // frame loop
 }
 
+
+// ---------------------------------------------------------------------------------------
+// k_exec_big: one CTA per large frame.  A frame's blocks and sequences are one sequential stream, so the
+// one-warp-per-frame kernel leaves a 17 MiB frame to a single warp.  Here BIG_WARPS warps take consecutive
+// 32-sequence chunks of a block round-robin.  A per-block pre-pass (chunk totals, one scan) gives every chunk its
+// literal and output offsets up front.  Chunks commit in order through two shared counters:
+//   * when a chunk starts, everything below `committed_out` is complete in dst, so matches whose source ends
+//     below it are copied right away (the common case for long-window data);
+//   * the rest (sources in chunks still in flight, or in this chunk) wait until all earlier chunks have
+//     committed and are then done in sequence order by the whole warp, exactly as in k_exec.
+// Same checks, same statuses, same results as k_exec; the first failing chunk in sequence order wins.
+// ---------------------------------------------------------------------------------------
+constexpr int BIG_WARPS = 8;
+constexpr uint32_t BIG_MAX_CHUNKS = 3072;  // n_seq <= 0x7F00 + 0xFFFF (sequence_section.cairo) -> at most 3065 chunks of 32
+
+struct BigSmem {
+    uint32_t chunk_lit[BIG_MAX_CHUNKS + 1];  // exclusive prefix of literal bytes per chunk, [n] = block total
+    uint32_t chunk_out[BIG_MAX_CHUNKS + 1];  // exclusive prefix of output bytes per chunk
+    __align__(16) uint8_t tile[BIG_WARPS][EXEC_TILE + 48];
+    unsigned long long committed_out;        // every output byte below this offset is in dst
+    uint32_t committed_chunks;               // chunks (numbered through the whole frame) committed so far
+    uint32_t err_chunk;                      // smallest failing chunk number, NONE32 if none
+    int32_t err_status;
+};
+
+__device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint64_t n, unsigned warp) {
+    const uint64_t per = ((n + BIG_WARPS - 1) / BIG_WARPS + 15) & ~15ull;
+    const uint64_t lo = (uint64_t)warp * per;
+    if (lo < n) warp_copy(dst + lo, src + lo, (uint32_t)(n - lo < per ? n - lo : per));
+}
+__device__ __forceinline__ void cta_fill(uint8_t* dst, uint8_t byte, uint64_t n, unsigned warp) {
+    const uint64_t per = ((n + BIG_WARPS - 1) / BIG_WARPS + 15) & ~15ull;
+    const uint64_t lo = (uint64_t)warp * per;
+    if (lo < n) warp_fill(dst + lo, byte, (uint32_t)(n - lo < per ? n - lo : per));
+}
+
+__global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
+                                                           uint32_t big_cls, uint32_t big_seq_bytes,
+                                                           const uint32_t* __restrict__ exec_order, BlockDesc* __restrict__ blocks,
+                                                           const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
+                                                           czb_frame_result* __restrict__ results) {
+    extern __shared__ __align__(16) uint8_t big_raw[];
+    BigSmem& sm = *reinterpret_cast<BigSmem*>(big_raw);
+    const unsigned warp = threadIdx.x >> 5, lane = lane_id();
+    const uint64_t f = exec_order[blockIdx.x];
+    const FrameInfo fi = infos[f];
+    if (fi.status != CZS_OK) return;  // k_header_results already reported it
+    if (!frame_is_big(fi, big_cls, big_seq_bytes)) return;  // k_exec's
+    const czb_frame_desc fd = descs[f];
+    const uint8_t* src = fd.src;
+    uint8_t* dst = fd.dst;
+    const uint64_t cap = fd.dst_cap < MAX_FRAME_OUT ? fd.dst_cap : MAX_FRAME_OUT;
+    const int32_t cap_status = fd.dst_cap < MAX_FRAME_OUT ? CZS_DST_TOO_SMALL : CZS_UNSUPPORTED;
+    volatile unsigned long long* v_out = &sm.committed_out;
+    volatile uint32_t* v_chunks = &sm.committed_chunks;
+    if (threadIdx.x == 0) { sm.committed_out = 0; sm.committed_chunks = 0; sm.err_chunk = NONE32; sm.err_status = CZS_OK; }
+    __syncthreads();
+
+    // every thread tracks the frame-level state identically (all of it is uniform)
+    uint64_t out = 0;
+    uint32_t h0 = 1, h1 = 4, h2 = 8;  // scratch.cairo:35
+    int32_t status = CZS_OK;
+    uint32_t n_done = 0, gc_base = 0;
+    uint64_t bytes_read = fi.hdr_len;
+    bool finished = false;
+
+    for (uint32_t k = 0; k < fi.n_blocks && status == CZS_OK; k++) {
+        const BlockDesc d = blocks[fi.block_base + k];
+        const uint64_t out_before = out;
+        if (d.type == BT_ERROR) { status = d.pre_status; break; }
+        if (d.type == BT_RAW) {
+            if (out + d.size > cap) { status = cap_status; break; }
+            cta_copy(dst + out, src + d.src_off, d.size, warp);
+            out += d.size; bytes_read += 3ull + d.size;
+        } else if (d.type == BT_RLE) {
+            if (out + d.size > cap) { status = cap_status; break; }
+            cta_fill(dst + out, src[d.src_off], d.size, warp);
+            out += d.size; bytes_read += 4;
+        } else {
+            // error order of decompress_block (:139-235): literals header, literals, sequences header, sequences, execution
+            if (d.pre_status != CZS_OK) { status = d.pre_status; break; }
+            if (d.lit_type >= LT_COMPRESSED && d.huf_status != CZS_OK) { status = d.huf_status; break; }
+            if (d.seqhdr_status != CZS_OK) { status = d.seqhdr_status; break; }
+            if (d.n_seq && d.fse_status != CZS_OK) { status = d.fse_status; break; }
+            const uint8_t* lits = d.lit_type >= LT_COMPRESSED ? lit_scratch + d.lit_off : src + d.lit_src_off;
+            const bool lit_rle = d.lit_type == LT_RLE;
+            const uint32_t rle_byte = lit_rle ? src[d.lit_src_off] : 0;
+            const uint32_t n_lit = d.regen;
+            const Seq* seqs = seq_scratch + d.seq_off;
+            const uint32_t n_chunks = (d.n_seq + 31) / 32;
+            // ---- pre-pass: literal and output bytes of every chunk, then one exclusive scan ----
+            for (uint32_t c = warp; c < n_chunks; c += BIG_WARPS) {
+                const uint32_t i = c * 32 + lane;
+                uint32_t ll = 0, ml = 0;
+                if (i < d.n_seq) { const Seq rec = seqs[i]; ll = seq_ll(rec); ml = seq_ml(rec); }
+                uint32_t ls = ll, os = ll + ml;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xFFFFFFFFu, ls, o); os += __shfl_xor_sync(0xFFFFFFFFu, os, o); }
+                if (lane == 0) { sm.chunk_lit[c] = ls; sm.chunk_out[c] = os; }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t cl = 0, co = 0;
+                for (uint32_t b = 0; b < n_chunks; b += 32) {
+                    const uint32_t c = b + lane;
+                    const uint32_t vl = c < n_chunks ? sm.chunk_lit[c] : 0u, vo = c < n_chunks ? sm.chunk_out[c] : 0u;
+                    uint32_t il = vl, io = vo;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, il, o), b2 = __shfl_up_sync(0xFFFFFFFFu, io, o);
+                        if ((int)lane >= o) { il += a; io += b2; }
+                    }
+                    if (c < n_chunks) { sm.chunk_lit[c] = cl + il - vl; sm.chunk_out[c] = co + io - vo; }
+                    cl += __shfl_sync(0xFFFFFFFFu, il, 31); co += __shfl_sync(0xFFFFFFFFu, io, 31);
+                }
+                if (lane == 0) { sm.chunk_lit[n_chunks] = cl; sm.chunk_out[n_chunks] = co; }
+            }
+            __syncthreads();
+            const uint32_t lit_total = sm.chunk_lit[n_chunks], out_total = sm.chunk_out[n_chunks];
+            // ---- chunks, round-robin over the warps, committed in order ----
+            for (uint32_t c = warp; c < n_chunks; c += BIG_WARPS) {
+                const uint32_t gc = gc_base + c;
+                const uint32_t i = c * 32 + lane;
+                const bool have = i < d.n_seq;
+                uint32_t ll = 0, ml = 0, off = 1;
+                if (have) { const Seq rec = __ldcs(seqs + i); ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
+                uint32_t lsum = ll, osum = ll + ml;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, lsum, o), b = __shfl_up_sync(0xFFFFFFFFu, osum, o);
+                    if ((int)lane >= o) { lsum += a; osum += b; }
+                }
+                const uint32_t lit_pos = sm.chunk_lit[c];
+                const uint64_t out_c = out + sm.chunk_out[c];
+                const uint32_t my_lit = lit_pos + lsum - ll, my_out = osum - ll - ml;
+                const uint32_t span = __shfl_sync(0xFFFFFFFFu, osum, 31);
+                // the reference's checks in its order (see k_exec); a failing chunk writes nothing but still commits
+                const uint64_t before_match = out_c + my_out + ll;
+                int32_t err = CZS_OK;
+                if (have) {
+                    if (ll > 0 && (uint64_t)my_lit + ll > n_lit) err = CZS_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE;  // :29-37
+                    else if (off == 0) err = CZS_EXEC_ZERO_OFFSET;                                            // :47-49
+                    else if (ml > 0 && off > before_match)                                                      // decode_buffer.cairo:65-93
+                        err = (before_match <= fi.window) ? CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY : CZS_OFFSET_TOO_BIG;
+                    else if (before_match + ml > cap) err = cap_status;
+                }
+                const unsigned errm = __ballot_sync(0xFFFFFFFFu, err != CZS_OK);
+                auto wait_prev = [&]() {
+                    while (*v_chunks != gc) __nanosleep(32);
+                    __threadfence_block();
+                };
+                if (errm) {
+                    const int32_t e = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1);
+                    wait_prev();  // every earlier chunk has committed: if one of them failed, its number is already there
+                    if (lane == 0 && gc < sm.err_chunk) { sm.err_chunk = gc; sm.err_status = e; }
+                } else if (span <= EXEC_TILE) {
+                    const unsigned long long avail = *v_out;  // a lower bound is fine: it only grows
+                    __threadfence_block();
+                    const uint64_t behind = out_c - (avail < out_c ? avail : out_c);
+                    const int avail_rel = -(int)(behind < 0x40000000ull ? behind : 0x40000000ull);
+                    exec_chunk_tile<true>(sm.tile[warp], dst + out_c, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span, avail_rel, wait_prev);
+                } else {
+                    // long segments: once everything before the chunk is in dst, one sequence at a time, the whole warp
+                    // copying straight into dst (overlapping matches as a repeated pattern, decode_buffer.cairo:101-120)
+                    wait_prev();
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t jl = __shfl_sync(0xFFFFFFFFu, ll, j), jm = __shfl_sync(0xFFFFFFFFu, ml, j), jo = __shfl_sync(0xFFFFFFFFu, off, j);
+                        const uint32_t jlit = __shfl_sync(0xFFFFFFFFu, my_lit, j), jout = __shfl_sync(0xFFFFFFFFu, my_out, j);
+                        uint8_t* o = dst + out_c + jout;
+                        if (jl) { if (lit_rle) warp_fill(o, (uint8_t)rle_byte, jl); else warp_copy(o, lits + jlit, jl); }
+                        o += jl;
+                        if (jm) {
+                            __syncwarp();
+                            if (jo >= jm) warp_copy(o, o - jo, jm);
+                            else for (uint32_t t = lane; t < jm; t += 32) o[t] = __ldcg(o - jo + (t % jo));
+                        }
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) { *v_out = out_c + span; __threadfence_block(); *v_chunks = gc + 1; }
+            }
+            __syncthreads();
+            if (sm.err_chunk != NONE32) { status = sm.err_status; break; }
+            gc_base += n_chunks;
+            out += out_total;
+            if (d.n_seq) {  // history after this block (resolved against the history it started from)
+                const uint32_t n0 = sym_is(d.hist_out[0]) ? sym_resolve(d.hist_out[0], h0, h1, h2) : d.hist_out[0];
+                const uint32_t n1 = sym_is(d.hist_out[1]) ? sym_resolve(d.hist_out[1], h0, h1, h2) : d.hist_out[1];
+                const uint32_t n2 = sym_is(d.hist_out[2]) ? sym_resolve(d.hist_out[2], h0, h1, h2) : d.hist_out[2];
+                h0 = n0; h1 = n1; h2 = n2;
+            }
+            // rest literals (:72-78), or all literals when there are no sequences (block_decoder.cairo:229-232)
+            const uint32_t rest = n_lit - lit_total;
+            if (rest) {
+                if (out + rest > cap) { status = cap_status; break; }
+                if (lit_rle) cta_fill(dst + out, (uint8_t)rle_byte, rest, warp);
+                else cta_copy(dst + out, lits + lit_total, rest, warp);
+                out += rest;
+            }
+            bytes_read += 3ull + d.size;
+        }
+        n_done++;
+        if (threadIdx.x == 0) blocks[fi.block_base + k].out_bytes = (uint32_t)(out - out_before);
+        if (d.last) {
+            finished = true;
+            if ((fi.descriptor >> 2) & 1) bytes_read += 4;
+        }
+        __syncthreads();  // the block's output (incl. raw/rle/rest copies by all warps) is complete in dst
+        if (threadIdx.x == 0) { *v_out = out; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        czb_frame_result r;
+        r.status = status;
+        r.blocks_decoded = n_done;
+        r.bytes_read = bytes_read;
+        r.bytes_written = status == CZS_OK ? out : 0;
+        r.content_size = fi.fcs;
+        r.window_size = fi.window;
+        r.checksum_from_data = fi.checksum;
+        r.checksum_calculated = 0;
+        r.has_checksum = fi.has_checksum;
+        r.finished = (status == CZS_OK && finished && (!((fi.descriptor >> 2) & 1) || fi.has_checksum)) ? 1 : 0;
+        results[f] = r;
+    }
+}
+
 static int exec_persistent_ctas() {
     static int n = 0;
     if (!n) {
@@ -433,13 +677,25 @@ static int exec_persistent_ctas() {
     return n;
 }
 
-void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_exec,
-                 WaveCounters* counters, const uint32_t* exec_order, BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
+void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_big_cls,
+                 uint32_t n_exec, uint32_t big_cls, uint32_t big_seq_bytes, WaveCounters* counters, const uint32_t* exec_order,
+                 BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
     if (!count || !n_exec) return;
+    // exec_order lists the wave's frames largest size class first.  k_exec_big gets one CTA for each of the first
+    // n_big_cls entries (the frames of at least 2^big_cls bytes) and takes those that pass frame_is_big; k_exec walks
+    // the whole list and skips exactly those.
     const uint64_t want = ((uint64_t)n_exec + EXEC_WARPS - 1) / EXEC_WARPS;
     const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
-    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, big_cls, big_seq_bytes, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
     ++*lc.launches;
+    if (n_big_cls) {
+        k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), lc.stream>>>(descs + first, infos + first, big_cls, big_seq_bytes, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+        ++*lc.launches;
+    }
+}
+
+int setup_exec_attributes() {
+    return (int)cudaFuncSetAttribute(k_exec_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem));
 }
 
 }  // namespace czb

@@ -157,6 +157,34 @@ def test_packed_host_path_chunks_and_error_frames(monkeypatch):
         assert dst[int(dst_off[k]):int(dst_off[k + 1])].tobytes() == origs[k], k
 
 
+def test_cta_per_frame_executor_forced_on_everything(corpus, monkeypatch):
+    """k_exec_big normally takes only large frames with sparse sequences; force every frame through it (valid, multi-block,
+    raw/RLE blocks, malformed) and compare with the oracle, status codes included."""
+    monkeypatch.setenv("CZB_BIG_CLS", "0")
+    monkeypatch.setenv("CZB_BIG_SEQ_BYTES", "0")
+    big = czb.Context(0)
+    frames = [corpus.frame(i) for i in range(len(corpus.index))]
+    caps = [e["orig_len"] + 16 for e in corpus.index]
+    f2, o2 = W.config2_text_frames(8, 65536)
+    f3, o3 = W.config3_literal_heavy(3)
+    f5, o5 = W.config5_mixed_sizes(10, hi=1 << 20)
+    for fs, os_ in ((f2, o2), (f3, o3), (f5, o5)):
+        frames += list(fs); caps += [len(o) for o in os_]
+    rng = np.random.default_rng(3)
+    for i in (5, 20, 43, 63):
+        f = corpus.frame(i)
+        for _ in range(10):
+            b = bytearray(f); pos = int(rng.integers(4, len(b))); b[pos] ^= 1 << int(rng.integers(0, 8))
+            frames.append(bytes(b)); caps.append(4 * corpus.index[i]["orig_len"] + 64)
+        frames.append(f[: len(f) // 2]); caps.append(corpus.index[i]["orig_len"] + 64)
+    outs, res = big.decode_batch(frames, caps, api.FLAG_VERIFY_CHECKSUM)
+    for k, f in enumerate(frames):
+        st, want, r = O.decode_frame(f, dst_cap=caps[k])
+        assert res[k].status == st, (k, czb.status_name(st), czb.status_name(res[k].status))
+        if st == 0:
+            assert outs[k] == want and res[k].bytes_read == r.bytes_read and res[k].blocks_decoded == r.blocks_decoded
+
+
 def test_empty_and_tiny_frames(corpus):
     cz = W.Compressor()
     origs = [b"", b"a", b"ab" * 3, b"\x00" * 70000, bytes(range(256)) * 3]
