@@ -97,12 +97,14 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
 // 16 source bytes starting at src (any alignment, global or shared memory) as four little-endian words.  Only the
 // aligned 32-bit words that hold one of the first n bytes are read.
 struct Vec16 { uint32_t v[4]; };
+template <bool CG = false>  // CG: read through L2 (data another warp of the CTA has just written)
 __device__ __forceinline__ Vec16 load16_unaligned(const uint8_t* __restrict__ src, uint32_t n) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(src);
     const uint32_t mis = (uint32_t)(a & 3), sh = mis * 8, need = n + mis;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
-    const uint32_t w0 = n ? w[0] : 0u;
-    const uint32_t w1 = need > 4 ? w[1] : 0u, w2 = need > 8 ? w[2] : 0u, w3 = need > 12 ? w[3] : 0u, w4 = need > 16 ? w[4] : 0u;
+    auto ld = [&](int k) -> uint32_t { return CG ? __ldcg(w + k) : w[k]; };
+    const uint32_t w0 = n ? ld(0) : 0u;
+    const uint32_t w1 = need > 4 ? ld(1) : 0u, w2 = need > 8 ? ld(2) : 0u, w3 = need > 12 ? ld(3) : 0u, w4 = need > 16 ? ld(4) : 0u;
     Vec16 r;
     r.v[0] = __funnelshift_r(w0, w1, sh); r.v[1] = __funnelshift_r(w1, w2, sh);
     r.v[2] = __funnelshift_r(w2, w3, sh); r.v[3] = __funnelshift_r(w3, w4, sh);
@@ -121,11 +123,12 @@ __device__ __forceinline__ void store16_to_tile(uint8_t* t, const Vec16& x, uint
 }
 
 // All lanes copy n bytes src -> tile + dst_off for the lane `j` that owns the job (arguments are taken from lane j).
+template <bool CG = false>
 __device__ __forceinline__ void coop_copy_to_tile(uint8_t* tile, unsigned lane, int j, uint32_t dst_off, const uint8_t* src, uint32_t n) {
     const uint32_t d = __shfl_sync(0xFFFFFFFFu, dst_off, j), cnt = __shfl_sync(0xFFFFFFFFu, n, j);
     const unsigned long long sp = __shfl_sync(0xFFFFFFFFu, (unsigned long long)reinterpret_cast<uintptr_t>(src), j);
     const uint8_t* s = reinterpret_cast<const uint8_t*>((uintptr_t)sp);
-    for (uint32_t i = lane; i < cnt; i += 32) tile[d + i] = s[i];
+    for (uint32_t i = lane; i < cnt; i += 32) tile[d + i] = CG ? __ldcg(s + i) : s[i];
 }
 
 // the same without the votes
@@ -142,12 +145,14 @@ __device__ __forceinline__ void store16_to_tile_all(uint8_t* t, const Vec16& x, 
 // avail_rel (<= 0) and wait_prev exist for k_exec_big, where several warps work on consecutive chunks of one frame:
 // output below obase + avail_rel is complete in dst when the call starts; wait_prev() returns once everything
 // below obase is.  The one-warp-per-frame kernel passes 0 and a no-op.
-// Which frames get a whole CTA (k_exec_big) instead of one warp (k_exec).  Large ones whose sequences are sparse:
-// with dense short matches nearly every chunk reads the output of the chunks just before it, the in-order commit
-// chain then serialises the warps and one warp per frame is faster (measured: text frames of 1..4 MiB 115 vs 54 GB/s,
-// long-window frames 12 vs 8 GB/s; literal-heavy 1 MiB frames 253 vs 365 GB/s the other way round).
-__device__ __forceinline__ bool frame_is_big(const FrameInfo& fi, uint32_t big_cls, uint32_t big_seq_bytes) {
-    return fi.size_cls >= big_cls && fi.n_seq * big_seq_bytes <= fi.src_end;
+// Which frames get a whole CTA (k_exec_big) instead of one warp (k_exec): large ones (>= 2^big_cls compressed bytes) that
+// either have sparse sequences (>= big_seq_bytes compressed bytes per sequence: literal-heavy data, long matches; the
+// warps then rarely wait for each other: 1 MiB literal-heavy frames 253 -> 371 GB/s) or are a large share of the wave
+// (>= 1/512 of its compressed bytes: one warp would still be on that frame long after the others have finished; with
+// dense short matches the in-order commit chain limits the gain: 17 MiB long-window frames 12 -> 16 GB/s, while
+// thousands of 1..4 MiB text frames are faster one warp each, 115 vs 103 GB/s).
+__device__ __forceinline__ bool frame_is_big(const FrameInfo& fi, uint32_t big_cls, uint32_t big_seq_bytes, uint64_t wave_share_bytes) {
+    return fi.size_cls >= big_cls && (fi.n_seq * big_seq_bytes <= fi.src_end || fi.src_end >= wave_share_bytes);
 }
 
 struct NoWait { __device__ __forceinline__ void operator()() const {} };
@@ -163,7 +168,7 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
     // first 16 bytes of every literal run and independent match: all loads are issued before the stores
     {
         const uint32_t nl = lit_rle ? 0u : (ll < 16u ? ll : 16u), nm = indep ? (ml < 16u ? ml : 16u) : 0u;
-        const Vec16 xl = load16_unaligned(lits + my_lit, nl), xm = load16_unaligned(msrc, nm);
+        const Vec16 xl = load16_unaligned(lits + my_lit, nl), xm = load16_unaligned<CG_LOADS>(msrc, nm);
         store16_to_tile(tile + segA, xl, nl);      // literal runs average under three bytes: later groups are usually skipped
         store16_to_tile_all(tile + segM, xm, nm);  // matches average nine: some lane always needs every group, votes only cost
     }
@@ -173,13 +178,27 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
         coop_copy_to_tile(tile, lane, __ffs(m) - 1, segA + 16u, lits + my_lit + 16, ll - 16u);
     if (lit_rle) for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, k < ll); k++) if (k < ll) tile[segA + k] = (uint8_t)rle_byte;
     for (unsigned m = __ballot_sync(0xFFFFFFFFu, indep && ml > 16u); m; m &= m - 1)
-        coop_copy_to_tile(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
+        coop_copy_to_tile<CG_LOADS>(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
     __syncwarp();
     wait_prev();
+    bool done = indep || ml == 0;
+    if (CG_LOADS) {
+        // k_exec_big: everything below obase is in dst now.  Matches whose source ends there but was not available
+        // when the chunk started are mutually independent: one more per-lane pass instead of one warp pass each.
+        const bool late = !done && segM + ml <= off;
+        const uint32_t nm = late ? (ml < 16u ? ml : 16u) : 0u;
+        if (__any_sync(0xFFFFFFFFu, late)) {
+            store16_to_tile(tile + segM, load16_unaligned<true>(msrc, nm), nm);
+            for (unsigned m = __ballot_sync(0xFFFFFFFFu, late && ml > 16u); m; m &= m - 1)
+                coop_copy_to_tile<true>(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
+            __syncwarp();
+        }
+        done = done || late;
+    }
     // Matches that read this chunk's own output (a few per chunk): in sequence order, the whole warp on each one, so
     // every source byte is final when it is read.  A match that overlaps itself (offset < length,
     // decode_buffer.cairo:101-120) repeats its first `offset` source bytes, which lie before its destination.
-    for (unsigned U = __ballot_sync(0xFFFFFFFFu, ml > 0 && !indep); U; U &= U - 1) {
+    for (unsigned U = __ballot_sync(0xFFFFFFFFu, !done); U; U &= U - 1) {
         const int j = __ffs(U) - 1;
         const uint32_t dM = __shfl_sync(0xFFFFFFFFu, segM, j), n = __shfl_sync(0xFFFFFFFFu, ml, j), o = __shfl_sync(0xFFFFFFFFu, off, j);
         const int s0 = (int)dM - (int)o;  // chunk-relative source start, may lie before the chunk (already in dst)
@@ -205,7 +224,7 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
 #endif
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
-                                                           uint64_t count, uint32_t big_cls, uint32_t big_seq_bytes, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
+                                                           uint64_t wave_share_bytes, uint32_t big_cls, uint32_t big_seq_bytes, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
                                                            BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
@@ -222,7 +241,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
     const uint64_t f = exec_order[qpos];  // largest frames first
     const FrameInfo fi = infos[f];
     if (fi.status != CZS_OK) continue;  // k_header_results already reported it
-    if (frame_is_big(fi, big_cls, big_seq_bytes)) continue;  // k_exec_big's
+    if (frame_is_big(fi, big_cls, big_seq_bytes, wave_share_bytes)) continue;  // k_exec_big's
     const czb_frame_desc fd = descs[f];
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
@@ -474,7 +493,7 @@ __device__ __forceinline__ void cta_fill(uint8_t* dst, uint8_t byte, uint64_t n,
 }
 
 __global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
-                                                           uint32_t big_cls, uint32_t big_seq_bytes,
+                                                           uint64_t wave_share_bytes, uint32_t big_cls, uint32_t big_seq_bytes,
                                                            const uint32_t* __restrict__ exec_order, BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
@@ -484,7 +503,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_des
     const uint64_t f = exec_order[blockIdx.x];
     const FrameInfo fi = infos[f];
     if (fi.status != CZS_OK) return;  // k_header_results already reported it
-    if (!frame_is_big(fi, big_cls, big_seq_bytes)) return;  // k_exec's
+    if (!frame_is_big(fi, big_cls, big_seq_bytes, wave_share_bytes)) return;  // k_exec's
     const czb_frame_desc fd = descs[f];
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
@@ -678,18 +697,20 @@ static int exec_persistent_ctas() {
 }
 
 void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_big_cls,
-                 uint32_t n_exec, uint32_t big_cls, uint32_t big_seq_bytes, WaveCounters* counters, const uint32_t* exec_order,
-                 BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
+                 uint32_t n_exec, uint32_t big_cls, uint32_t big_seq_bytes, uint64_t wave_src_bytes, WaveCounters* counters,
+                 const uint32_t* exec_order, BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch,
+                 czb_frame_result* results) {
     if (!count || !n_exec) return;
+    const uint64_t wave_share_bytes = big_seq_bytes ? wave_src_bytes / 512 + 1 : 0;  // big_seq_bytes == 0 (test knob): every large frame
     // exec_order lists the wave's frames largest size class first.  k_exec_big gets one CTA for each of the first
     // n_big_cls entries (the frames of at least 2^big_cls bytes) and takes those that pass frame_is_big; k_exec walks
     // the whole list and skips exactly those.
     const uint64_t want = ((uint64_t)n_exec + EXEC_WARPS - 1) / EXEC_WARPS;
     const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
-    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, count, big_cls, big_seq_bytes, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, wave_share_bytes, big_cls, big_seq_bytes, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
     ++*lc.launches;
     if (n_big_cls) {
-        k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), lc.stream>>>(descs + first, infos + first, big_cls, big_seq_bytes, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+        k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), lc.stream>>>(descs + first, infos + first, wave_share_bytes, big_cls, big_seq_bytes, exec_order, blocks, lit_scratch, seq_scratch, results + first);
         ++*lc.launches;
     }
 }
