@@ -468,7 +468,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
 //     committed and are then done in sequence order by the whole warp, exactly as in k_exec.
 // Same checks, same statuses, same results as k_exec; the first failing chunk in sequence order wins.
 // ---------------------------------------------------------------------------------------
-constexpr int BIG_WARPS = 8;
+#ifndef CZB_BIG_WARPS
+#define CZB_BIG_WARPS 4  // swept 4/8/16: literal-heavy 1 MiB frames 398/367/346 GB/s, 17 MiB long-window frames 15.9/16.5/15.4 GB/s
+#endif
+constexpr int BIG_WARPS = CZB_BIG_WARPS;
 constexpr uint32_t BIG_MAX_CHUNKS = 3072;  // n_seq <= 0x7F00 + 0xFFFF (sequence_section.cairo) -> at most 3065 chunks of 32
 
 struct BigSmem {

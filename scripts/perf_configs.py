@@ -63,12 +63,16 @@ def main():
     dev = torch.device("cuda", 0)
     ctx = czb.Context(0)
     outs = []
-    f, o = W.config3_literal_heavy(16)
-    outs.append(run("config3 literal-heavy 1 MiB frames", f, o, 64, ctx, dev))
-    f, o = W.config5_mixed_sizes(512, hi=4 << 20)
-    outs.append(run("config5 mixed 1 KiB..4 MiB", f, o, 16, ctx, dev))
-    f, o = W.config4_long_window(2, total=17 << 20)
-    outs.append(run("config4 long window 17 MiB frames", f, o, 32, ctx, dev))
+    only = sys.argv[1] if len(sys.argv) > 1 else ""  # "3", "4" or "5": just that configuration
+    if only in ("", "3"):
+        f, o = W.config3_literal_heavy(16)
+        outs.append(run("config3 literal-heavy 1 MiB frames", f, o, 64, ctx, dev))
+    if only in ("", "5"):
+        f, o = W.config5_mixed_sizes(512, hi=4 << 20)
+        outs.append(run("config5 mixed 1 KiB..4 MiB", f, o, 16, ctx, dev))
+    if only in ("", "4"):
+        f, o = W.config4_long_window(2, total=17 << 20)
+        outs.append(run("config4 long window 17 MiB frames", f, o, 32, ctx, dev))
     json.dump(outs, open(os.path.join(ROOT, "gpurun_out", "perf_configs.json"), "w"), indent=1)
 
 
