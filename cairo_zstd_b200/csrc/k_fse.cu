@@ -199,7 +199,16 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
     uint32_t h0, h1, h2;
     if (sl.first_in_frame) { h0 = 1; h1 = 4; h2 = 8; }  // scratch.cairo:35
     else { h0 = sym_enc(0); h1 = sym_enc(1); h2 = sym_enc(2); }
-    if (st == CZS_OK) {
+    // The decode loop exists twice.  The fast form only notes THAT something went wrong (two ORs per step); a block for
+    // which it did is decoded again by the exact form, which records WHICH error came first, in the reference's order
+    // (two compares and selects per step: 8 % of the kernel when it was always on).
+    const uint32_t h_in0 = h0, h_in1 = h1, h_in2 = h2;
+    auto decode = [&](auto exact_tag) -> int32_t {
+    constexpr bool EXACT = decltype(exact_tag)::value;
+    int32_t st = CZS_OK;
+    uint32_t trouble = 0;  // fast form: bit 31 set <=> a bad code or an over-read happened somewhere
+    h0 = h_in0; h1 = h_in1; h2 = h_in2;
+    {
         // phase 1's scratch is dead now (the other warps have left): it becomes the lanes' bitstream rings
         RevBitsWin br;
         const bool init_ok = br.init(sl.bits, (int)sl.bits_len, (uint32_t)__cvta_generic_to_shared(sm.tmp) + lane * RevBitsWin::RING);
@@ -235,9 +244,13 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 br.step_sync();
                 const uint32_t ofc = fse_entry_sym(eOF);
                 // :235-237; codes beyond the tables give (0,255) -> TooManyBits
-                const bool bad_code = ((ofc >> 5) | ((lle | mle) >> 31)) != 0;
-                const int32_t code_status = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
-                st = (st == CZS_OK && bad_code) ? code_status : st;
+                if (EXACT) {
+                    const bool bad_code = ((ofc >> 5) | ((lle | mle) >> 31)) != 0;
+                    const int32_t code_status = ofc >= 32 ? CZS_SEQ_UNSUPPORTED_OFFSET : CZS_SEQ_GET_BITS_ERROR;
+                    st = (st == CZS_OK && bad_code) ? code_status : st;
+                } else {
+                    trouble |= (ofc << 26) | lle | mle;  // ofc >= 32 puts its bit 5 at bit 31
+                }
                 const uint32_t llb = (lle >> 20) & 31u, mlb = (mle >> 20) & 31u, ofb = ofc & 31u;
                 const uint32_t extras = ofb + mlb + llb;  // <= 63 bits, read in the order OF, ML, LL (:239)
                 // The three state updates (LL, ML, OF, <= 26 bits, :258-276) come from their own 32-bit window below the
@@ -284,14 +297,22 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                     nbLL = fse_entry_nbits(eLL, logLL); nbML = fse_entry_nbits(eML, logML); nbOF = fse_entry_nbits(eOF, logOF);
                 }
                 // :281-283; the no-RLE variant traps on the unwrap at :279 instead
-                st = (st == CZS_OK && br.rem() < 0) ? short_status : st;
+                if (EXACT) st = (st == CZS_OK && br.rem() < 0) ? short_status : st;
+                else trouble |= (uint32_t)br.rem();  // negative <=> bit 31
             };
             uint32_t i = 0;
 #pragma unroll 4
             for (; i + 1 < n_seq; i++) step(i, std::true_type{});
             step(i, std::false_type{});
+            if (!EXACT && (trouble >> 31)) st = CZS_NOT_DECODED;  // placeholder: the exact form decides
             if (st == CZS_OK && br.rem() > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
         }
+    }
+    return st;
+    };
+    if (st == CZS_OK) {
+        st = decode(std::false_type{});
+        if (st == CZS_NOT_DECODED) st = decode(std::true_type{});
     }
     BlockDesc& d = blocks[sl.blk];
     d.fse_status = st;
