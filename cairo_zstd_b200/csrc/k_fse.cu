@@ -239,8 +239,9 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             RevBitsWin::Raw64 win = br.window64_raw();
             const uint32_t dummy = (uint32_t)__cvta_generic_to_shared(sm.tmp) + FSE_SLOTS * RevBitsWin::RING + lane * 16u;
             uint32_t nbLL = fse_entry_nbits(eLL, logLL), nbML = fse_entry_nbits(eML, logML), nbOF = fse_entry_nbits(eOF, logOF);
-            auto step = [&](uint32_t i, auto more_tag) {
+            auto step = [&](uint32_t i, auto more_tag, auto refill_tag) {
                 constexpr bool MORE = decltype(more_tag)::value;
+                constexpr int REFILLS = decltype(refill_tag)::value;  // ring slots to look after in this step
                 br.step_sync();
                 const uint32_t ofc = fse_entry_sym(eOF);
                 // :235-237; codes beyond the tables give (0,255) -> TooManyBits
@@ -266,7 +267,8 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                     const uint32_t z = RevBitsWin::window_of(winB);
                     aLL = shr_clamp(z, 32u - nbLL); aML = shr_clamp(z << nbLL, 32u - nbML); aOF = shr_clamp(z << (nbLL + nbML), 32u - nbOF);
                     br.P -= (int)(extras + nbLL + nbML + nbOF);
-                    br.refill_nobranch(dummy);
+#pragma unroll
+                    for (int r = 0; r < REFILLS; r++) br.refill_nobranch(dummy);
                     win = br.window64_raw();  // the next step's bits: three LDS issued next to the state lookups below
                 } else {
                     br.P -= (int)extras;
@@ -300,10 +302,16 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 if (EXACT) st = (st == CZS_OK && br.rem() < 0) ? short_status : st;
                 else trouble |= (uint32_t)br.rem();  // negative <=> bit 31
             };
+            // Four steps consume at most 356 bits, i.e. leave at most three 16-byte chunks behind: the ring is looked after
+            // once per four steps (three always-issued cp.async) instead of once per step.
+            using R0 = std::integral_constant<int, 0>; using R1 = std::integral_constant<int, 1>; using R3 = std::integral_constant<int, 3>;
             uint32_t i = 0;
-#pragma unroll 4
-            for (; i + 1 < n_seq; i++) step(i, std::true_type{});
-            step(i, std::false_type{});
+            for (; i + 4 < n_seq; i += 4) {
+                step(i, std::true_type{}, R0{}); step(i + 1, std::true_type{}, R0{});
+                step(i + 2, std::true_type{}, R0{}); step(i + 3, std::true_type{}, R3{});
+            }
+            for (; i + 1 < n_seq; i++) step(i, std::true_type{}, R1{});
+            step(i, std::false_type{}, R0{});
             if (!EXACT && (trouble >> 31)) st = CZS_NOT_DECODED;  // placeholder: the exact form decides
             if (st == CZS_OK && br.rem() > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
         }
