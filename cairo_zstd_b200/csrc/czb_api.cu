@@ -62,6 +62,9 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     // and whose sequences are sparse (at least big_seq_bytes compressed bytes per sequence; 0 = any).  Knobs for tests.
     if (const char* e = getenv("CZB_BIG_CLS")) ctx->big_cls = atoi(e);
     if (const char* e = getenv("CZB_BIG_SEQ_BYTES")) ctx->big_seq_bytes = atoi(e);
+    if (const char* e = getenv("CZB_SHARE_CLS")) ctx->share_cls = atoi(e);
+    if (const char* e = getenv("CZB_BIG_SHARE")) ctx->big_share = atoi(e) > 0 ? atoi(e) : 1;
+    if (ctx->share_cls > ctx->big_cls) ctx->share_cls = ctx->big_cls;
     // Planning read-back buffer: host memory mapped into the device address space.  A kernel writes the
     // per-wave totals straight into it, so the read-back never queues behind a large device-to-host
     // copy on the copy engine (that serialised decode behind the previous chunk's output transfer).
@@ -75,6 +78,13 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
         if (cudaEventCreateWithFlags(&ctx->ev_entropy[s], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_exec[s], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
     if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    {
+        int lo = 0, hi = 0;  // k_exec_big's CTAs first: the largest frames are the long pole of a wave
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&ctx->big_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_big_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_big_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+    }
     *out = ctx;
     return CZS_OK;
 }
@@ -92,6 +102,9 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
         if (ctx->ev_exec[s]) cudaEventDestroy(ctx->ev_exec[s]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_big_fork) cudaEventDestroy(ctx->ev_big_fork);
+    if (ctx->ev_big_join) cudaEventDestroy(ctx->ev_big_join);
+    if (ctx->big_stream) cudaStreamDestroy(ctx->big_stream);
     if (ctx->exec_stream) cudaStreamDestroy(ctx->exec_stream);
     cudaFree(ctx->h_descs.p); cudaFree(ctx->h_results.p);
     for (int s = 0; s < czb_context::kHostSlots; s++) { cudaFree(ctx->h_src[s].p); cudaFree(ctx->h_dst[s].p); }
@@ -212,7 +225,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
         const WaveTotals& t = ctx->totals_h[w];
         uint32_t n_exec = 0, n_big = 0;
-        for (int c = 0; c < 32; c++) { n_exec += t.frame_cls[c]; if (c >= ctx->big_cls) n_big += t.frame_cls[c]; }
+        for (int c = 0; c < 32; c++) { n_exec += t.frame_cls[c]; if (c >= ctx->share_cls) n_big += t.frame_cls[c]; }
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
         { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0); }
@@ -222,7 +235,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
             CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
-        { ProfScope ps(ctx, xs, 4); launch_exec(lx, descs, ctx->infos.p, first, count, n_big, n_exec, (uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint64_t)t.src_bytes, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join}, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, ctx->big_seq_bytes ? (uint64_t)t.src_bytes / (uint64_t)ctx->big_share + 1 : 0}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;

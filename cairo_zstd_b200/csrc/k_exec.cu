@@ -20,6 +20,8 @@
 //     the row's segment map.
 // HBM traffic per frame: literals + 8 B/sequence in, decoded bytes out; match sources are recent output (L1/L2 when the
 // in-flight working set allows, DRAM otherwise: profiles/r01_final_ncu_summary.md).
+#include <cstdio>
+
 #include "czb_internal.cuh"
 
 namespace czb {
@@ -145,17 +147,26 @@ __device__ __forceinline__ void store16_to_tile_all(uint8_t* t, const Vec16& x, 
 // avail_rel (<= 0) and wait_prev exist for k_exec_big, where several warps work on consecutive chunks of one frame:
 // output below obase + avail_rel is complete in dst when the call starts; wait_prev() returns once everything
 // below obase is.  The one-warp-per-frame kernel passes 0 and a no-op.
-// Which frames get a whole CTA (k_exec_big) instead of one warp (k_exec): large ones (>= 2^big_cls compressed bytes) that
-// either have sparse sequences (>= big_seq_bytes compressed bytes per sequence: literal-heavy data, long matches; the
-// warps then rarely wait for each other: 1 MiB literal-heavy frames 253 -> 371 GB/s) or are a large share of the wave
-// (>= 1/512 of its compressed bytes: one warp would still be on that frame long after the others have finished; with
-// dense short matches the in-order commit chain limits the gain: 17 MiB long-window frames 12 -> 16 GB/s, while
-// thousands of 1..4 MiB text frames are faster one warp each, 115 vs 103 GB/s).
-__device__ __forceinline__ bool frame_is_big(const FrameInfo& fi, uint32_t big_cls, uint32_t big_seq_bytes, uint64_t wave_share_bytes) {
-    return fi.size_cls >= big_cls && (fi.n_seq * big_seq_bytes <= fi.src_end || fi.src_end >= wave_share_bytes);
+// Which frames get a whole CTA (k_exec_big) instead of one warp (k_exec):
+//  * large ones (>= 2^big_cls compressed bytes) with sparse sequences (>= big_seq_bytes compressed bytes per sequence:
+//    literal-heavy data, long matches), whose warps rarely wait for each other (1 MiB literal-heavy frames 253 -> 400 GB/s);
+//  * from 2^share_cls bytes on, frames that hold at least 1/big_share of the wave's compressed bytes.  A frame is one
+//    sequential stream; on one warp among ~4000 it moves at ~1/4000 of the machine's rate, so a frame with more than
+//    about 1/8000 of the wave's bytes is still running when everything else has finished.  A CTA moves it two to three
+//    times faster (the in-order commit chain of k_exec_big is the limit) and runs beside k_exec on its own stream.
+//    (mixed 1 KiB..4 MiB frames: 118 -> 150 GB/s; a batch of equal frames never qualifies.)
+__device__ __forceinline__ bool frame_is_big(const FrameInfo& fi, const BigRule& r) {
+    return (fi.size_cls >= r.big_cls && fi.n_seq * r.big_seq_bytes <= fi.src_end) || (fi.size_cls >= r.share_cls && fi.src_end >= r.share_bytes);
 }
 
 struct NoWait { __device__ __forceinline__ void operator()() const {} };
+// Measurement aid (-DCZB_BIG_CLOCK): cycles per phase of k_exec_big, accumulated by thread 0 of CTA 0 and printed per launch.
+#ifdef CZB_BIG_CLOCK
+__device__ unsigned long long czb_dbg_clk[16];
+#define CLK_MARK(k) do { if (dbg) { const long long t_ = clock64(); atomicAdd(&czb_dbg_clk[k], (unsigned long long)(t_ - *dbg)); *dbg = t_; } } while (0)
+#else
+#define CLK_MARK(k) do { } while (0)
+#endif
 template <bool CG_LOADS, typename WaitPrev>
 __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* obase, const uint8_t* __restrict__ lits, bool lit_rle,
                                                 uint32_t rle_byte, unsigned lane, uint32_t ll, uint32_t ml, uint32_t off,
@@ -221,10 +232,150 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
     if (lane < tail) obase[head + (nv << 4) + lane] = tile[head + (nv << 4) + lane];
     __syncwarp();
 }
+
+// ---- k_exec_big's chunk executor: the frame's recent output lives in a shared-memory window ----
+// k_exec_big commits the chunks of a frame in order, so whatever a chunk does between "everything before me is
+// complete" and "I am complete" is a serial chain that every other warp of the CTA waits for.  With the chunk built in
+// a private tile and handed over through dst, that chain held two global round trips (clock64, 17 MiB long-window
+// frames, cycles per chunk: late-source loads from L2 1190, in-chunk dependent matches 830, flush 340, and 2050 for the
+// fence that makes the flushed bytes visible before the commit counter moves).  Here every chunk is built in place in
+// a CTA-wide window indexed by the low bits of its dst address: later chunks read recent output from the window, the
+// chunk commits as soon as its slice is complete, and the copy to dst happens after the commit, off the chain.
+//
+// Validity: the window holds the output of the current block from `lo_rel` (chunk-relative, <= 0) on: the block start,
+// or WIN_REACH bytes back.  Older bytes are read from dst: bytes before the block were published by a CTA barrier, bytes
+// more than WIN_REACH back were flushed at least 15 chunks ago by a warp that has since passed a fence and a commit
+// which this warp has observed.  A block with a chunk longer than the tile does not use the window (k_exec_big falls
+// back to exec_chunk_tile for it), so consecutive in-flight slices never alias.
+constexpr uint32_t BIG_WIN = 16384, BIG_WIN_MASK = BIG_WIN - 1;
+// How far below a chunk's start the window is trusted: the other warps may be building the next BIG_WARPS - 1 chunks, whose
+// slices must not alias what this one reads.  (BIG_WARPS_MAX bounds CZB_BIG_WARPS.)
+constexpr int BIG_WARPS_MAX = 8;
+constexpr int BIG_WIN_REACH = (int)BIG_WIN - 64 - BIG_WARPS_MAX * (int)EXEC_TILE;
+
+struct WinView {
+    uint8_t* win;     // BIG_WIN bytes of shared memory, 16-byte aligned
+    uint8_t* obase;   // dst address of chunk-relative position 0
+    uint32_t gb;      // low 32 bits of obase: window index of position x is (gb + x) & BIG_WIN_MASK
+    int lo_rel;       // positions >= lo_rel are in the window, older ones only in dst
+    __device__ __forceinline__ uint32_t idx(int x) const { return (gb + (uint32_t)x) & BIG_WIN_MASK; }
+    __device__ __forceinline__ uint8_t rd(int x) const { return x >= lo_rel ? win[idx(x)] : __ldcg(obase + x); }
+    // first n (<= 16) bytes from position x, which lie in the window
+    __device__ __forceinline__ Vec16 load16(int x, uint32_t n) const {
+        const uint32_t a = gb + (uint32_t)x, mis = a & 3u, sh = mis * 8u, need = n + mis;
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(win);
+        const uint32_t wi = a >> 2;
+        auto ld = [&](uint32_t k) -> uint32_t { return w32[(wi + k) & (BIG_WIN / 4 - 1)]; };
+        const uint32_t w0 = n ? ld(0) : 0u;
+        const uint32_t w1 = need > 4 ? ld(1) : 0u, w2 = need > 8 ? ld(2) : 0u, w3 = need > 12 ? ld(3) : 0u, w4 = need > 16 ? ld(4) : 0u;
+        Vec16 r;
+        r.v[0] = __funnelshift_r(w0, w1, sh); r.v[1] = __funnelshift_r(w1, w2, sh);
+        r.v[2] = __funnelshift_r(w2, w3, sh); r.v[3] = __funnelshift_r(w3, w4, sh);
+        return r;
+    }
+    __device__ __forceinline__ void store16(int x, const Vec16& v, uint32_t n) const {
+        const uint32_t a = gb + (uint32_t)x;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (g == 0 || __any_sync(0xFFFFFFFFu, n > 4u * g)) {
+#pragma unroll
+                for (int k = 4 * g; k < 4 * g + 4; k++) if ((uint32_t)k < n) win[(a + k) & BIG_WIN_MASK] = (uint8_t)(v.v[g] >> (8 * (k & 3)));
+            }
+        }
+    }
+};
+
+// Same contract as exec_chunk_tile (lane = sequence, chunk span <= EXEC_TILE); publish() commits the chunk.
+template <typename WaitPrev, typename Publish>
+__device__ __forceinline__ void exec_chunk_win(uint8_t* win, uint8_t* obase, int lo_rel, const uint8_t* __restrict__ lits, bool lit_rle,
+                                               uint32_t rle_byte, unsigned lane, uint32_t ll, uint32_t ml, uint32_t off,
+                                               uint32_t my_lit, uint32_t segA, uint32_t span, int avail_rel, WaitPrev wait_prev, Publish publish,
+                                               long long* dbg) {
+    WinView W{win, obase, (uint32_t)reinterpret_cast<uintptr_t>(obase), lo_rel};
+    const uint32_t segM = segA + ll;
+    const int s_lo = (int)segM - (int)off;       // chunk-relative source start of the match
+    const int s_end = s_lo + (int)ml;            // the match is complete below the chunk iff s_end <= 0 (then off >= ml)
+    const uint8_t* msrc = obase + s_lo;
+    // literal runs: first 16 bytes per lane, tails by the whole warp
+    {
+        const uint32_t nl = lit_rle ? 0u : (ll < 16u ? ll : 16u);
+        W.store16((int)segA, load16_unaligned(lits + my_lit, nl), nl);
+    }
+    for (unsigned m = __ballot_sync(0xFFFFFFFFu, !lit_rle && ll > 16u); m; m &= m - 1) {
+        const int j = __ffs(m) - 1;
+        const uint32_t d = __shfl_sync(0xFFFFFFFFu, segA, j) + 16u, cnt = __shfl_sync(0xFFFFFFFFu, ll, j) - 16u, lp = __shfl_sync(0xFFFFFFFFu, my_lit, j) + 16u;
+        for (uint32_t i = lane; i < cnt; i += 32) win[W.idx((int)(d + i))] = lits[lp + i];
+    }
+    if (lit_rle) for (uint32_t k = 0; __any_sync(0xFFFFFFFFu, k < ll); k++) if (k < ll) win[W.idx((int)(segA + k))] = (uint8_t)rle_byte;
+    // matches whose whole source lies below the chunk and is complete: `pred` selects them (those available when the chunk
+    // starts, then, after the wait, the rest).  Source in the window or in dst per lane; a source that straddles the
+    // window's lower edge goes byte by byte.
+    auto copy_far = [&](bool pred) {
+        const bool in_win = pred && s_lo >= lo_rel, in_dst = pred && s_end <= lo_rel;
+        const uint32_t nm = (in_win || in_dst) ? (ml < 16u ? ml : 16u) : 0u;
+        const Vec16 xw = W.load16(in_win ? s_lo : 0, in_win ? nm : 0u), xg = load16_unaligned<true>(msrc, in_dst ? nm : 0u);
+        Vec16 x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) x.v[k] = in_win ? xw.v[k] : xg.v[k];
+        W.store16((int)segM, x, nm);
+        // tails and straddling sources: the whole warp on one match at a time
+        for (unsigned m = __ballot_sync(0xFFFFFFFFu, pred && (ml > 16u || nm == 0u)); m; m &= m - 1) {
+            const int j = __ffs(m) - 1;
+            const uint32_t dM = __shfl_sync(0xFFFFFFFFu, segM, j), n = __shfl_sync(0xFFFFFFFFu, ml, j), skip = __shfl_sync(0xFFFFFFFFu, nm, j);
+            const int s0 = __shfl_sync(0xFFFFFFFFu, s_lo, j);
+            for (uint32_t i = skip + lane; i < n; i += 32) win[W.idx((int)(dM + i))] = W.rd(s0 + (int)i);
+        }
+    };
+#ifdef CZB_WHATIF_NOFAR
+    const bool indep = ml > 0 && s_end <= avail_rel && span == 0xFFFFFFFFu;
+#else
+    const bool indep = ml > 0 && s_end <= avail_rel;
+#endif
+    copy_far(indep);
+    __syncwarp();
+    CLK_MARK(2);
+    wait_prev();
+    CLK_MARK(3);
+    const bool late = ml > 0 && !indep && s_end <= 0;
+    if (__any_sync(0xFFFFFFFFu, late)) { copy_far(late); __syncwarp(); }
+    CLK_MARK(4);
+    // Matches that read this chunk's own output: in sequence order, the whole warp on each one, so every source byte is
+    // final when it is read.  A match that overlaps itself (offset < length, decode_buffer.cairo:101-120) repeats its
+    // first `offset` source bytes, which lie before its destination.
+    for (unsigned U = __ballot_sync(0xFFFFFFFFu, ml > 0 && s_end > 0); U; U &= U - 1) {
+        const int j = __ffs(U) - 1;
+        const uint32_t dM = __shfl_sync(0xFFFFFFFFu, segM, j), n = __shfl_sync(0xFFFFFFFFu, ml, j), o = __shfl_sync(0xFFFFFFFFu, off, j);
+        const int s0 = (int)dM - (int)o;
+        if (o >= n && s0 >= 0) {  // the usual case: source inside the chunk, no self-overlap
+            for (uint32_t i = lane; i < n; i += 32) win[W.idx((int)(dM + i))] = win[W.idx(s0 + (int)i)];
+        } else if (o >= n) {
+            for (uint32_t i = lane; i < n; i += 32) win[W.idx((int)(dM + i))] = W.rd(s0 + (int)i);
+        } else {
+            for (uint32_t i = lane; i < n; i += 32) win[W.idx((int)(dM + i))] = W.rd(s0 + (int)(i % o));
+        }
+        __syncwarp();
+    }
+    CLK_MARK(5);
+    publish();  // the slice is complete: later chunks may read it from the window
+    CLK_MARK(7);
+    // copy to dst, off the commit chain: aligned 16-byte stores (window index and dst address agree modulo 16)
+#ifdef CZB_WHATIF_NOFLUSH
+    if (span != 0xFFFFFFFFu) return;
+#endif
+    const uint32_t a0 = W.gb & 15u;
+    const uint32_t head = span < ((16 - a0) & 15) ? span : ((16 - a0) & 15);
+    if (lane < head) obase[lane] = win[W.idx((int)lane)];
+    const uint32_t body = span - head, nv = body >> 4, tail = body & 15;
+    uint4* g4 = reinterpret_cast<uint4*>(obase + head);
+    for (uint32_t v = lane; v < nv; v += 32) g4[v] = *reinterpret_cast<const uint4*>(win + W.idx((int)(head + (v << 4))));
+    if (lane < tail) obase[head + (nv << 4) + lane] = win[W.idx((int)(head + (nv << 4) + lane))];
+    __syncwarp();
+    CLK_MARK(6);
+}
 #endif
 
 __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
-                                                           uint64_t wave_share_bytes, uint32_t big_cls, uint32_t big_seq_bytes, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
+                                                           BigRule rule, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
                                                            BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
@@ -241,7 +392,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
     const uint64_t f = exec_order[qpos];  // largest frames first
     const FrameInfo fi = infos[f];
     if (fi.status != CZS_OK) continue;  // k_header_results already reported it
-    if (frame_is_big(fi, big_cls, big_seq_bytes, wave_share_bytes)) continue;  // k_exec_big's
+    if (frame_is_big(fi, rule)) continue;  // k_exec_big's
     const czb_frame_desc fd = descs[f];
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
@@ -468,21 +619,44 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
 //     committed and are then done in sequence order by the whole warp, exactly as in k_exec.
 // Same checks, same statuses, same results as k_exec; the first failing chunk in sequence order wins.
 // ---------------------------------------------------------------------------------------
+#ifndef CZB_BIG_WIN
+#define CZB_BIG_WIN 1  // 0: always the tile + dst hand-over (measurement aid)
+#endif
+constexpr bool BIG_USE_WIN = CZB_BIG_WIN != 0;
+#ifndef CZB_BIG_POLL_NS
+#define CZB_BIG_POLL_NS 32
+#endif
+constexpr unsigned BIG_POLL_NS = CZB_BIG_POLL_NS;
 #ifndef CZB_BIG_WARPS
 #define CZB_BIG_WARPS 4  // swept 4/8/16: literal-heavy 1 MiB frames 398/367/346 GB/s, 17 MiB long-window frames 15.9/16.5/15.4 GB/s
 #endif
 constexpr int BIG_WARPS = CZB_BIG_WARPS;
-constexpr uint32_t BIG_MAX_CHUNKS = 3072;  // n_seq <= 0x7F00 + 0xFFFF (sequence_section.cairo) -> at most 3065 chunks of 32
+#ifndef CZB_BIG_MIN_CTAS
+#define CZB_BIG_MIN_CTAS 7  // 72 registers, no spills; ~25 KB of shared memory per CTA
+#endif
+constexpr int BIG_MIN_CTAS = CZB_BIG_MIN_CTAS;
+static_assert(BIG_WARPS <= BIG_WARPS_MAX && BIG_WARPS * (EXEC_TILE + 48) <= BIG_WIN, "window reach and tile carve-out assume at most BIG_WARPS_MAX warps");
+constexpr uint32_t BIG_BATCH = 1024;  // chunks per batch (n_seq <= 0x7F00 + 0xFFFF, sequence_section.cairo: at most 3065 chunks per block)
 
 struct BigSmem {
-    uint32_t chunk_lit[BIG_MAX_CHUNKS + 1];  // exclusive prefix of literal bytes per chunk, [n] = block total
-    uint32_t chunk_out[BIG_MAX_CHUNKS + 1];  // exclusive prefix of output bytes per chunk
-    __align__(16) uint8_t tile[BIG_WARPS][EXEC_TILE + 48];
-    unsigned long long committed_out;        // every output byte below this offset is in dst
+    uint32_t chunk_lit[BIG_BATCH + 4];  // exclusive prefix of literal bytes per chunk of the batch, [n] = batch total
+    uint32_t chunk_out[BIG_BATCH + 4];  // exclusive prefix of output bytes per chunk of the batch
+    __align__(16) uint8_t win[BIG_WIN];      // recent output of the current block (exec_chunk_win); per-warp tiles for a block with long chunks
+    unsigned long long committed_out;        // every output byte below this offset is complete (in the window or in dst)
+    uint32_t n_long;                         // chunks of the current batch that are longer than a window slice
+    uint16_t long_idx[BIG_BATCH];            // their indices, ascending
     uint32_t committed_chunks;               // chunks (numbered through the whole frame) committed so far
     uint32_t err_chunk;                      // smallest failing chunk number, NONE32 if none
     int32_t err_status;
 };
+
+// __threadfence_block() is membar.cta = fence.sc.cta, a sequentially consistent fence: several hundred cycles each, and
+// k_exec_big has four of them on every chunk.  Acquire/release ordering is all the commit protocol needs.
+#ifndef CZB_BIG_SC_FENCE
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+#else
+__device__ __forceinline__ void fence_cta() { __threadfence_block(); }
+#endif
 
 __device__ __forceinline__ void cta_copy(uint8_t* dst, const uint8_t* src, uint64_t n, unsigned warp) {
     const uint64_t per = ((n + BIG_WARPS - 1) / BIG_WARPS + 15) & ~15ull;
@@ -495,8 +669,8 @@ __device__ __forceinline__ void cta_fill(uint8_t* dst, uint8_t byte, uint64_t n,
     if (lo < n) warp_fill(dst + lo, byte, (uint32_t)(n - lo < per ? n - lo : per));
 }
 
-__global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
-                                                           uint64_t wave_share_bytes, uint32_t big_cls, uint32_t big_seq_bytes,
+__global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const czb_frame_desc* __restrict__ descs, const FrameInfo* __restrict__ infos,
+                                                           BigRule rule,
                                                            const uint32_t* __restrict__ exec_order, BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
                                                            czb_frame_result* __restrict__ results) {
@@ -506,7 +680,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_des
     const uint64_t f = exec_order[blockIdx.x];
     const FrameInfo fi = infos[f];
     if (fi.status != CZS_OK) return;  // k_header_results already reported it
-    if (!frame_is_big(fi, big_cls, big_seq_bytes, wave_share_bytes)) return;  // k_exec's
+    if (!frame_is_big(fi, rule)) return;  // k_exec's
     const czb_frame_desc fd = descs[f];
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
@@ -525,7 +699,14 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_des
     uint64_t bytes_read = fi.hdr_len;
     bool finished = false;
 
+#ifdef CZB_BIG_CLOCK
+    long long dbg_t0 = clock64();
+    long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? &dbg_t0 : nullptr;
+#else
+    long long* dbg = nullptr;
+#endif
     for (uint32_t k = 0; k < fi.n_blocks && status == CZS_OK; k++) {
+        CLK_MARK(9);
         const BlockDesc d = blocks[fi.block_base + k];
         const uint64_t out_before = out;
         if (d.type == BT_ERROR) { status = d.pre_status; break; }
@@ -549,50 +730,83 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_des
             const uint32_t n_lit = d.regen;
             const Seq* seqs = seq_scratch + d.seq_off;
             const uint32_t n_chunks = (d.n_seq + 31) / 32;
-            // ---- pre-pass: literal and output bytes of every chunk, then one exclusive scan ----
-            for (uint32_t c = warp; c < n_chunks; c += BIG_WARPS) {
-                const uint32_t i = c * 32 + lane;
-                uint32_t ll = 0, ml = 0;
-                if (i < d.n_seq) { const Seq rec = seqs[i]; ll = seq_ll(rec); ml = seq_ml(rec); }
-                uint32_t ls = ll, os = ll + ml;
+            // A block's chunks are taken in batches of BIG_BATCH (the two prefix tables stay small, so that seven CTAs fit an
+            // SM; a block of text has ~250 chunks, i.e. one batch).
+            uint32_t lit_total = 0, out_total = 0;  // literal / output bytes of the batches done so far
+            for (uint32_t cb = 0; cb < n_chunks && sm.err_chunk == NONE32; cb += BIG_BATCH) {
+            const uint32_t nb = n_chunks - cb < BIG_BATCH ? n_chunks - cb : BIG_BATCH;
+            // ---- pre-pass: literal and output bytes of every chunk of the batch, then one exclusive scan ----
+            // (four chunks per iteration so that four record loads are in flight: the loop is a chain of global round trips)
+            for (uint32_t q0 = warp * 4; q0 < nb; q0 += BIG_WARPS * 4) {
+                Seq rec[4];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xFFFFFFFFu, ls, o); os += __shfl_xor_sync(0xFFFFFFFFu, os, o); }
-                if (lane == 0) { sm.chunk_lit[c] = ls; sm.chunk_out[c] = os; }
+                for (int q = 0; q < 4; q++) { const uint32_t i = (cb + q0 + q) * 32 + lane; rec[q] = i < d.n_seq ? seqs[i] : 0ull; }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    uint32_t ls = seq_ll(rec[q]), os = ls + seq_ml(rec[q]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xFFFFFFFFu, ls, o); os += __shfl_xor_sync(0xFFFFFFFFu, os, o); }
+                    if (lane == 0 && q0 + q < nb) { sm.chunk_lit[q0 + q] = ls; sm.chunk_out[q0 + q] = os; }
+                }
             }
             __syncthreads();
             if (warp == 0) {
-                uint32_t cl = 0, co = 0;
-                for (uint32_t b = 0; b < n_chunks; b += 32) {
+                uint32_t cl = 0, co = 0, n_long = 0;
+                for (uint32_t b = 0; b < nb; b += 32) {
                     const uint32_t c = b + lane;
-                    const uint32_t vl = c < n_chunks ? sm.chunk_lit[c] : 0u, vo = c < n_chunks ? sm.chunk_out[c] : 0u;
+                    const uint32_t vl = c < nb ? sm.chunk_lit[c] : 0u, vo = c < nb ? sm.chunk_out[c] : 0u;
+                    const unsigned lm = __ballot_sync(0xFFFFFFFFu, vo > EXEC_TILE);  // chunks that do not fit a window slice
+                    if (vo > EXEC_TILE) sm.long_idx[n_long + __popc(lm & lanemask_lt())] = (uint16_t)c;
+                    n_long += __popc(lm);
                     uint32_t il = vl, io = vo;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
                         const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, il, o), b2 = __shfl_up_sync(0xFFFFFFFFu, io, o);
                         if ((int)lane >= o) { il += a; io += b2; }
                     }
-                    if (c < n_chunks) { sm.chunk_lit[c] = cl + il - vl; sm.chunk_out[c] = co + io - vo; }
+                    if (c < nb) { sm.chunk_lit[c] = cl + il - vl; sm.chunk_out[c] = co + io - vo; }
                     cl += __shfl_sync(0xFFFFFFFFu, il, 31); co += __shfl_sync(0xFFFFFFFFu, io, 31);
                 }
-                if (lane == 0) { sm.chunk_lit[n_chunks] = cl; sm.chunk_out[n_chunks] = co; }
+                if (lane == 0) { sm.chunk_lit[nb] = cl; sm.chunk_out[nb] = co; sm.n_long = n_long; }
             }
             __syncthreads();
-            const uint32_t lit_total = sm.chunk_lit[n_chunks], out_total = sm.chunk_out[n_chunks];
-            // ---- chunks, round-robin over the warps, committed in order ----
-            for (uint32_t c = warp; c < n_chunks; c += BIG_WARPS) {
+            const uint32_t lit_batch = sm.chunk_lit[nb], out_batch = sm.chunk_out[nb];
+            const uint32_t n_long = sm.n_long;
+            CLK_MARK(0);
+            // ---- chunks, committed in order.  A chunk that fits a window slice (the usual case) goes round-robin over the
+            // warps; a long one is done by warp 0 alone between two CTA barriers, straight into dst, and the window starts
+            // afresh after it: so all slices in flight at any time lie within BIG_WARPS * EXEC_TILE bytes and never alias,
+            // and what the window does not hold was made visible by a barrier. ----
+            uint32_t seg = 0;  // first chunk of the current run of window chunks
+            for (uint32_t kl = 0; kl <= n_long && seg < nb; kl++) {
+            const uint32_t L = kl < n_long ? sm.long_idx[kl] : nb;  // the long chunk that ends the run (nb: none)
+            const uint32_t seg_out0 = sm.chunk_out[seg];
+            for (int pass = 0; pass < 2; pass++) {
+            const uint32_t q_lo = pass == 0 ? seg + warp : (warp == 0 ? L : nb), q_hi = pass == 0 ? L : (L < nb ? L + 1 : L);
+            for (uint32_t q = q_lo; q < q_hi; q += BIG_WARPS) {
+                const uint32_t c = cb + q;
                 const uint32_t gc = gc_base + c;
                 const uint32_t i = c * 32 + lane;
                 const bool have = i < d.n_seq;
                 uint32_t ll = 0, ml = 0, off = 1;
+                CLK_MARK(10);
                 if (have) { const Seq rec = __ldcs(seqs + i); ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
+#ifdef CZB_BIG_CLOCK
+                if (dbg && ll == 0xFFFFFFFFu) printf("x");
+#endif
+                CLK_MARK(11);
                 uint32_t lsum = ll, osum = ll + ml;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, lsum, o), b = __shfl_up_sync(0xFFFFFFFFu, osum, o);
                     if ((int)lane >= o) { lsum += a; osum += b; }
                 }
-                const uint32_t lit_pos = sm.chunk_lit[c];
-                const uint64_t out_c = out + sm.chunk_out[c];
+#ifdef CZB_BIG_CLOCK
+                if (dbg && osum == 0xFFFFFFFFu) printf("y");
+#endif
+                CLK_MARK(12);
+                const uint32_t lit_pos = lit_total + sm.chunk_lit[q];
+                const uint64_t out_c = out + out_total + sm.chunk_out[q];
                 const uint32_t my_lit = lit_pos + lsum - ll, my_out = osum - ll - ml;
                 const uint32_t span = __shfl_sync(0xFFFFFFFFu, osum, 31);
                 // the reference's checks in its order (see k_exec); a failing chunk writes nothing but still commits
@@ -606,43 +820,81 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_des
                     else if (before_match + ml > cap) err = cap_status;
                 }
                 const unsigned errm = __ballot_sync(0xFFFFFFFFu, err != CZS_OK);
+                CLK_MARK(1);
                 auto wait_prev = [&]() {
-                    while (*v_chunks != gc) __nanosleep(32);
-                    __threadfence_block();
+                    while (*v_chunks != gc) __nanosleep(BIG_POLL_NS);
+                    fence_cta();
+                };
+                auto publish = [&]() {
+                    __syncwarp();
+                    if (lane == 0) { fence_cta(); *v_out = out_c + span; fence_cta(); *v_chunks = gc + 1; }
                 };
                 if (errm) {
                     const int32_t e = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1);
                     wait_prev();  // every earlier chunk has committed: if one of them failed, its number is already there
                     if (lane == 0 && gc < sm.err_chunk) { sm.err_chunk = gc; sm.err_status = e; }
+                    publish();
                 } else if (span <= EXEC_TILE) {
                     const unsigned long long avail = *v_out;  // a lower bound is fine: it only grows
-                    __threadfence_block();
+                    fence_cta();
                     const uint64_t behind = out_c - (avail < out_c ? avail : out_c);
                     const int avail_rel = -(int)(behind < 0x40000000ull ? behind : 0x40000000ull);
-                    exec_chunk_tile<true>(sm.tile[warp], dst + out_c, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span, avail_rel, wait_prev);
+                    if (BIG_USE_WIN) {
+                        const uint32_t in_run = sm.chunk_out[q] - seg_out0;  // bytes of this run before the chunk: all of them went through the window
+                        const int lo_rel = -(int)(in_run < (uint32_t)BIG_WIN_REACH ? in_run : (uint32_t)BIG_WIN_REACH);
+                        exec_chunk_win(sm.win, dst + out_c, lo_rel, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span, avail_rel, wait_prev, publish, dbg);
+                    } else {
+                        exec_chunk_tile<true>(sm.win + warp * (EXEC_TILE + 48), dst + out_c, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span, avail_rel, wait_prev);
+                        __syncwarp();
+                        fence_cta();  // the flushed bytes are visible to the CTA before the commit
+                        publish();
+                    }
                 } else {
-                    // long segments: once everything before the chunk is in dst, one sequence at a time, the whole warp
-                    // copying straight into dst (overlapping matches as a repeated pattern, decode_buffer.cairo:101-120)
+                    // A chunk that does not fit a slice: once everything before it is in dst, it is cut at sequence boundaries
+                    // into pieces that do fit (each executed like a chunk of its own, through a tile, with the lanes outside
+                    // the piece idle); a single sequence that does not fit is copied straight into dst by the whole warp
+                    // (overlapping matches as a repeated pattern, decode_buffer.cairo:101-120).
                     wait_prev();
-                    for (int j = 0; j < 32; j++) {
-                        const uint32_t jl = __shfl_sync(0xFFFFFFFFu, ll, j), jm = __shfl_sync(0xFFFFFFFFu, ml, j), jo = __shfl_sync(0xFFFFFFFFu, off, j);
-                        const uint32_t jlit = __shfl_sync(0xFFFFFFFFu, my_lit, j), jout = __shfl_sync(0xFFFFFFFFu, my_out, j);
-                        uint8_t* o = dst + out_c + jout;
-                        if (jl) { if (lit_rle) warp_fill(o, (uint8_t)rle_byte, jl); else warp_copy(o, lits + jlit, jl); }
-                        o += jl;
-                        if (jm) {
-                            __syncwarp();
-                            if (jo >= jm) warp_copy(o, o - jo, jm);
-                            else for (uint32_t t = lane; t < jm; t += 32) o[t] = __ldcg(o - jo + (t % jo));
+                    for (uint32_t start = 0; start < 32;) {
+                        const uint32_t base_o = __shfl_sync(0xFFFFFFFFu, my_out, start);
+                        const unsigned fit = __ballot_sync(0xFFFFFFFFu, lane >= start && my_out + ll + ml - base_o <= EXEC_TILE);
+                        if (!((fit >> start) & 1u)) {
+                            const int j = (int)start;
+                            const uint32_t jl = __shfl_sync(0xFFFFFFFFu, ll, j), jm = __shfl_sync(0xFFFFFFFFu, ml, j), jo = __shfl_sync(0xFFFFFFFFu, off, j);
+                            const uint32_t jlit = __shfl_sync(0xFFFFFFFFu, my_lit, j);
+                            uint8_t* o = dst + out_c + base_o;
+                            if (jl) { if (lit_rle) warp_fill(o, (uint8_t)rle_byte, jl); else warp_copy(o, lits + jlit, jl); }
+                            o += jl;
+                            if (jm) {
+                                __syncwarp();
+                                fence_cta();
+                                if (jo >= jm) warp_copy(o, o - jo, jm);
+                                else for (uint32_t t = lane; t < jm; t += 32) o[t] = __ldcg(o - jo + (t % jo));
+                            }
+                            start++;
+                        } else {
+                            const uint32_t last = 31u - (uint32_t)__clz(fit);  // fit is a run of lanes from `start` (offsets only grow)
+                            const bool in = lane >= start && lane <= last;
+                            const uint32_t span_p = __shfl_sync(0xFFFFFFFFu, my_out + ll + ml, last) - base_o;
+                            exec_chunk_tile<true>(sm.win, dst + out_c + base_o, lits, lit_rle, rle_byte, lane, in ? ll : 0u, in ? ml : 0u, off, my_lit,
+                                                  in ? my_out - base_o : 0u, span_p, 0, NoWait{});
+                            start = last + 1;
                         }
                         __syncwarp();
+                        fence_cta();  // the next piece reads this one's bytes from dst
                     }
+                    __syncwarp();
+                    fence_cta();
+                    publish();
                 }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) { *v_out = out_c + span; __threadfence_block(); *v_chunks = gc + 1; }
             }
-            __syncthreads();
+            __syncthreads();  // everything up to here is complete in dst and visible to the whole CTA
+            }  // pass
+            seg = L + 1;
+            }  // runs of window chunks
+            CLK_MARK(8);
+            lit_total += lit_batch; out_total += out_batch;
+            }  // batch loop
             if (sm.err_chunk != NONE32) { status = sm.err_status; break; }
             gc_base += n_chunks;
             out += out_total;
@@ -686,6 +938,15 @@ __global__ void __launch_bounds__(BIG_WARPS * 32) k_exec_big(const czb_frame_des
         r.finished = (status == CZS_OK && finished && (!((fi.descriptor >> 2) & 1) || fi.has_checksum)) ? 1 : 0;
         results[f] = r;
     }
+#ifdef CZB_BIG_CLOCK
+    if (dbg) {
+        CLK_MARK(9);
+        printf("big clk: prepass %llu | rec+prefix %llu | first pass %llu | wait %llu | late %llu | in-chunk %llu | flush %llu | publish %llu | block end %llu | block start/raw/rest %llu\n",
+               czb_dbg_clk[0], czb_dbg_clk[1], czb_dbg_clk[2], czb_dbg_clk[3], czb_dbg_clk[4], czb_dbg_clk[5], czb_dbg_clk[6], czb_dbg_clk[7], czb_dbg_clk[8], czb_dbg_clk[9]);
+        printf("   loop top %llu | rec load %llu | prefix %llu\n", czb_dbg_clk[10], czb_dbg_clk[11], czb_dbg_clk[12]);
+        for (int q = 0; q < 16; q++) czb_dbg_clk[q] = 0;
+    }
+#endif
 }
 
 static int exec_persistent_ctas() {
@@ -699,23 +960,27 @@ static int exec_persistent_ctas() {
     return n;
 }
 
-void launch_exec(const LaunchCtx& lc, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_big_cls,
-                 uint32_t n_exec, uint32_t big_cls, uint32_t big_seq_bytes, uint64_t wave_src_bytes, WaveCounters* counters,
+void launch_exec(const LaunchCtx& lc, const ExecSide& side, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_big_cls,
+                 uint32_t n_exec, BigRule rule, WaveCounters* counters,
                  const uint32_t* exec_order, BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch,
                  czb_frame_result* results) {
     if (!count || !n_exec) return;
-    const uint64_t wave_share_bytes = big_seq_bytes ? wave_src_bytes / 512 + 1 : 0;  // big_seq_bytes == 0 (test knob): every large frame
     // exec_order lists the wave's frames largest size class first.  k_exec_big gets one CTA for each of the first
-    // n_big_cls entries (the frames of at least 2^big_cls bytes) and takes those that pass frame_is_big; k_exec walks
-    // the whole list and skips exactly those.
-    const uint64_t want = ((uint64_t)n_exec + EXEC_WARPS - 1) / EXEC_WARPS;
-    const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
-    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, wave_share_bytes, big_cls, big_seq_bytes, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
-    ++*lc.launches;
+    // n_big_cls entries (the frames of at least 2^min(big_cls, share_cls) bytes) and takes those that pass frame_is_big;
+    // k_exec walks the whole list and skips exactly those.  The two kernels run side by side: k_exec_big on its own
+    // (higher priority) stream, forked from and joined to the caller's.
     if (n_big_cls) {
-        k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), lc.stream>>>(descs + first, infos + first, wave_share_bytes, big_cls, big_seq_bytes, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+        cudaEventRecord(side.fork, lc.stream);
+        cudaStreamWaitEvent(side.stream, side.fork, 0);
+        k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), side.stream>>>(descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+        cudaEventRecord(side.join, side.stream);
         ++*lc.launches;
     }
+    const uint64_t want = ((uint64_t)n_exec + EXEC_WARPS - 1) / EXEC_WARPS;
+    const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
+    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, rule, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+    ++*lc.launches;
+    if (n_big_cls) cudaStreamWaitEvent(lc.stream, side.join, 0);
 }
 
 int setup_exec_attributes() {

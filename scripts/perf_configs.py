@@ -47,14 +47,20 @@ def run(name, frames, origs, reps, ctx, dev):
     e1.record(st)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
+    ctx.profile_enable(True)  # per-kernel-class times of one more pass (events around every launch)
+    ctx.decode_batch_device(descs.data_ptr(), results.data_ptr(), n, 0, st.cuda_stream)
+    torch.cuda.synchronize()
+    kernel_ms = {k: round(v[0], 3) for k, v in ctx.profile_collect().items()}
+    ctx.profile_enable(False)
     res = results.cpu().numpy().view(np.dtype([("status", "<i4"), ("b", "<u4"), ("br", "<u8"), ("bw", "<u8"), ("cs", "<u8"), ("w", "<u8"),
                                                ("c1", "<u4"), ("c2", "<u4"), ("h", "<i4"), ("f", "<i4")]))
-    assert (res["status"] == 0).all(), name
-    for k in (0, n - 1):
+    nocheck = bool(os.environ.get("CZB_PERF_NOCHECK"))  # what-if builds that compute something wrong on purpose
+    assert nocheck or (res["status"] == 0).all(), name
+    for k in (() if nocheck else (0, n - 1)):
         o = int(d[k, 2] - dst.data_ptr())
         assert dst[o:o + int(olens[k % n0])].cpu().numpy().tobytes() == origs[k % n0], (name, k)
     out = {"config": name, "frames": n, "out_GB": float(olens.sum() * reps / 1e9), "ratio": float(olens.sum() / flens.sum()),
-           "ms": ms, "GBps": float(olens.sum() * reps / ms / 1e6)}
+           "ms": ms, "GBps": float(olens.sum() * reps / ms / 1e6), "kernel_ms": kernel_ms}
     print(json.dumps(out), flush=True)
     return out
 
