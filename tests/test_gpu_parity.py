@@ -185,6 +185,43 @@ def test_cta_per_frame_executor_forced_on_everything(corpus, monkeypatch):
             assert outs[k] == want and res[k].bytes_read == r.bytes_read and res[k].blocks_decoded == r.blocks_decoded
 
 
+def _giant_and_mixed_frames():
+    """Frames whose chunks mix tiny and very long segments: periodic data (one self-overlapping match of ~100 KiB per
+    block, offsets 1, 2 and 1000), long literal runs followed by long repeats, and text with 4 KiB repeats spliced in
+    (so that tile-sized chunks and long ones alternate inside a block)."""
+    rng = np.random.default_rng(11)
+    cz = W.Compressor()
+    blob = rng.integers(0, 256, 1000, dtype=np.uint8).tobytes()
+    text = W.synth_text(300000, 7)
+    spliced = bytearray()
+    pos = 0
+    while pos < len(text) - 9000:
+        spliced += text[pos:pos + 3000]
+        spliced += text[max(0, pos - 20000):max(0, pos - 20000) + 4096]  # a long repeat of older material
+        pos += 3000
+    origs = [b"a" * 300000, b"ab" * 150000, blob * 300, blob + b"\x00" * 5000 + blob * 40 + bytes(rng.integers(0, 256, 70000, dtype=np.uint8)) + blob * 100,
+             bytes(spliced), bytes(spliced[:70000]) * 4]
+    return [cz.compress(o) for o in origs], origs
+
+
+def test_giant_sequences_and_mixed_chunk_lengths():
+    frames, origs = _giant_and_mixed_frames()
+    outs, _ = compare_with_oracle(frames, [len(o) for o in origs], label="giant")
+    for o, w in zip(outs, origs):
+        assert o == w
+
+
+def test_giant_sequences_through_the_cta_per_frame_executor(monkeypatch):
+    monkeypatch.setenv("CZB_BIG_CLS", "0")
+    monkeypatch.setenv("CZB_BIG_SEQ_BYTES", "0")
+    big = czb.Context(0)
+    frames, origs = _giant_and_mixed_frames()
+    outs, res = big.decode_batch(frames, [len(o) for o in origs], api.FLAG_VERIFY_CHECKSUM)
+    for k, o in enumerate(origs):
+        assert res[k].status == 0 and outs[k] == o, k
+        assert res[k].checksum_calculated == res[k].checksum_from_data
+
+
 def test_empty_and_tiny_frames(corpus):
     cz = W.Compressor()
     origs = [b"", b"a", b"ab" * 3, b"\x00" * 70000, bytes(range(256)) * 3]
