@@ -65,6 +65,11 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     if (const char* e = getenv("CZB_SHARE_CLS")) ctx->share_cls = atoi(e);
     if (const char* e = getenv("CZB_BIG_SHARE")) ctx->big_share = atoi(e) > 0 ? atoi(e) : 1;
     if (ctx->share_cls > ctx->big_cls) ctx->share_cls = ctx->big_cls;
+    {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        ctx->big_resident = 7 * sms;  // k_exec_big CTAs that fit the machine at once (72 registers x 128 threads)
+    }
     // Planning read-back buffer: host memory mapped into the device address space.  A kernel writes the
     // per-wave totals straight into it, so the read-back never queues behind a large device-to-host
     // copy on the copy engine (that serialised decode behind the previous chunk's output transfer).
@@ -226,6 +231,15 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         const WaveTotals& t = ctx->totals_h[w];
         uint32_t n_exec = 0, n_big = 0;
         for (int c = 0; c < 32; c++) { n_exec += t.frame_cls[c]; if (c >= ctx->share_cls) n_big += t.frame_cls[c]; }
+        // Share rule of k_exec_big (see frame_is_big): frames that hold at least 1/big_share of the wave's compressed bytes.
+        // A CTA per frame only pays while the CTAs all fit the machine at once (seven per SM): with more frames than that
+        // in the wave, only frames well above the mean qualify, so a large batch of equal frames stays with k_exec
+        // (4096 equal 256 KiB frames: 2.4 ms one warp each, 5.3 ms one CTA each; 1024 of them: 1.6 against 1.4 ms).
+        uint64_t share_bytes = 0;  // big_seq_bytes == 0 (test knob): every frame of the class
+        if (ctx->big_seq_bytes) {
+            share_bytes = (uint64_t)t.src_bytes / (uint64_t)ctx->big_share + 1;
+            if (count > (uint64_t)ctx->big_resident) share_bytes = std::max<uint64_t>(share_bytes, (uint64_t)t.src_bytes * 3 / (2 * count) + 1);
+        }
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
         { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0); }
@@ -235,7 +249,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
             CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
-        { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join}, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, ctx->big_seq_bytes ? (uint64_t)t.src_bytes / (uint64_t)ctx->big_share + 1 : 0}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join}, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;

@@ -76,6 +76,9 @@ def main():
     if only in ("", "5"):
         f, o = W.config5_mixed_sizes(512, hi=4 << 20)
         outs.append(run("config5 mixed 1 KiB..4 MiB", f, o, 16, ctx, dev))
+    if only == "6":  # not a BASELINE config: a mid-size batch of equal frames, to check the k_exec_big share rule
+        f, o = W.config2_text_frames(64, 262144)
+        outs.append(run("equal 256 KiB text frames", f, o, int(os.environ.get("CZB_PERF_REPS", "64")), ctx, dev))
     if only in ("", "4"):
         f, o = W.config4_long_window(2, total=17 << 20)
         outs.append(run("config4 long window 17 MiB frames", f, o, 32, ctx, dev))
