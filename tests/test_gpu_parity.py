@@ -157,6 +157,26 @@ def test_packed_host_path_chunks_and_error_frames(monkeypatch):
         assert dst[int(dst_off[k]):int(dst_off[k + 1])].tobytes() == origs[k], k
 
 
+def test_tightly_packed_buffers_any_alignment(corpus):
+    """The packed path keeps the caller's offsets on the device: corpus frames and outputs back to back, so that sources
+    and destinations start at every alignment (unaligned match copies, flushes and the unaligned XXH64 read path)."""
+    import ctypes as C
+    frames = [corpus.frame(i) for i in range(len(corpus.index))]
+    lens = [e["orig_len"] for e in corpus.index]
+    n = len(frames)
+    src = np.frombuffer(b"\x00" + b"".join(frames), dtype=np.uint8).copy()
+    src_off = np.ones(n + 1, dtype=np.uint64); src_off[1:] += np.cumsum([len(f) for f in frames]).astype(np.uint64)
+    dst_off = np.full(n + 1, 3, dtype=np.uint64); dst_off[1:] += np.cumsum(lens).astype(np.uint64)
+    dst = np.zeros(int(dst_off[-1]) + 8, dtype=np.uint8)
+    results = (api.FrameResult * n)()
+    ctx().decode_batch_packed(src.ctypes.data, src_off, dst.ctypes.data, dst_off, n, C.addressof(results), api.FLAG_VERIFY_CHECKSUM)
+    assert len({int(o) & 7 for o in dst_off[:-1]}) == 8
+    for k in range(n):
+        assert results[k].status == 0 and results[k].bytes_written == lens[k], k
+        assert sha(dst[int(dst_off[k]):int(dst_off[k + 1])].tobytes()) == corpus.index[k]["orig_sha256"], k
+        assert results[k].has_checksum and results[k].checksum_calculated == results[k].checksum_from_data, k
+
+
 def test_cta_per_frame_executor_forced_on_everything(corpus, monkeypatch):
     """k_exec_big normally takes only large frames with sparse sequences; force every frame through it (valid, multi-block,
     raw/RLE blocks, malformed) and compare with the oracle, status codes included."""
