@@ -326,11 +326,7 @@ __device__ __forceinline__ void exec_chunk_win(uint8_t* win, uint8_t* obase, int
             for (uint32_t i = skip + lane; i < n; i += 32) win[W.idx((int)(dM + i))] = W.rd(s0 + (int)i);
         }
     };
-#ifdef CZB_WHATIF_NOFAR
-    const bool indep = ml > 0 && s_end <= avail_rel && span == 0xFFFFFFFFu;
-#else
     const bool indep = ml > 0 && s_end <= avail_rel;
-#endif
     copy_far(indep);
     __syncwarp();
     CLK_MARK(2);
@@ -359,9 +355,6 @@ __device__ __forceinline__ void exec_chunk_win(uint8_t* win, uint8_t* obase, int
     publish();  // the slice is complete: later chunks may read it from the window
     CLK_MARK(7);
     // copy to dst, off the commit chain: aligned 16-byte stores (window index and dst address agree modulo 16)
-#ifdef CZB_WHATIF_NOFLUSH
-    if (span != 0xFFFFFFFFu) return;
-#endif
     const uint32_t a0 = W.gb & 15u;
     const uint32_t head = span < ((16 - a0) & 15) ? span : ((16 - a0) & 15);
     if (lane < head) obase[lane] = win[W.idx((int)lane)];
@@ -792,7 +785,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
                 CLK_MARK(10);
                 if (have) { const Seq rec = __ldcs(seqs + i); ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
 #ifdef CZB_BIG_CLOCK
-                if (dbg && ll == 0xFFFFFFFFu) printf("x");
+                if (dbg && ll == 0xFFFFFFFFu) printf("x");  // consume the record before the mark: the load's latency belongs to this phase
 #endif
                 CLK_MARK(11);
                 uint32_t lsum = ll, osum = ll + ml;
@@ -802,7 +795,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
                     if ((int)lane >= o) { lsum += a; osum += b; }
                 }
 #ifdef CZB_BIG_CLOCK
-                if (dbg && osum == 0xFFFFFFFFu) printf("y");
+                if (dbg && osum == 0xFFFFFFFFu) printf("y");  // likewise for the prefix sums
 #endif
                 CLK_MARK(12);
                 const uint32_t lit_pos = lit_total + sm.chunk_lit[q];
@@ -941,9 +934,9 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
 #ifdef CZB_BIG_CLOCK
     if (dbg) {
         CLK_MARK(9);
-        printf("big clk: prepass %llu | rec+prefix %llu | first pass %llu | wait %llu | late %llu | in-chunk %llu | flush %llu | publish %llu | block end %llu | block start/raw/rest %llu\n",
+        printf("big clk: prepass %llu | checks %llu | first pass %llu | wait %llu | late %llu | in-chunk %llu | flush %llu | publish %llu | block end %llu | block start/raw/rest %llu\n",
                czb_dbg_clk[0], czb_dbg_clk[1], czb_dbg_clk[2], czb_dbg_clk[3], czb_dbg_clk[4], czb_dbg_clk[5], czb_dbg_clk[6], czb_dbg_clk[7], czb_dbg_clk[8], czb_dbg_clk[9]);
-        printf("   loop top %llu | rec load %llu | prefix %llu\n", czb_dbg_clk[10], czb_dbg_clk[11], czb_dbg_clk[12]);
+        printf("   loop top + long chunks %llu | rec load %llu | prefix %llu\n", czb_dbg_clk[10], czb_dbg_clk[11], czb_dbg_clk[12]);
         for (int q = 0; q < 16; q++) czb_dbg_clk[q] = 0;
     }
 #endif
