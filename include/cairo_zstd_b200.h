@@ -86,7 +86,10 @@ int czb_abi_version(void);
  * entries; every src/dst inside descs is a DEVICE pointer.  Work is enqueued on
  * `stream` (a cudaStream_t passed as void*; NULL = default stream).  The call itself
  * synchronises `stream` internally once (a small planning read-back) and returns after
- * the last kernel is enqueued, not after it finished.
+ * the last kernel is enqueued, not after it finished.  Some kernels run on streams owned by
+ * the context, forked from and joined back to `stream` with events: work enqueued on
+ * `stream` after the call sees every result; a context must not be used from two host
+ * threads at once (as the reference's FrameDecoder, it is not shareable).
  * Replaces: one FrameDecoderStateTrait::new + FrameDecoderTrait::new + decode_blocks(All) +
  * collect() per frame (src/tests/decoding.cairo:4-21). */
 int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results,
