@@ -51,6 +51,8 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     ctx->device = device;
     ctx->budget = budget ? budget : (12ull << 30);
     ctx->wave_frames = 131072;
+    if (const char* e = getenv("CZB_WAVE_FRAMES")) ctx->wave_frames = (uint64_t)atoll(e) > 128 ? (uint64_t)atoll(e) : 128;  // tuning knobs
+    if (const char* e = getenv("CZB_BUDGET_GB")) ctx->budget = (uint64_t)atoll(e) << 30;
     // Wave pipelining over two streams is opt-in (CZB_OVERLAP=1): measured on B200 it gains ~1 % because the
     // entropy kernels and k_exec contend for the same issue slots and registers, and it makes the per-kernel
     // event times overlap.  Default: one stream, every kernel alone, exact per-kernel timings.
