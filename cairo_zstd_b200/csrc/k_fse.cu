@@ -21,7 +21,10 @@
 
 namespace czb {
 
-constexpr int FSE_WARPS = 4;
+#ifndef CZB_FSE_WARPS
+#define CZB_FSE_WARPS 4  // table-building warps per CTA (6 / 8 measured: see DESIGN.md)
+#endif
+constexpr int FSE_WARPS = CZB_FSE_WARPS;
 #ifndef CZB_FSE_SLOTS
 #define CZB_FSE_SLOTS 27
 #endif
