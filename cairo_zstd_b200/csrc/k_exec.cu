@@ -242,11 +242,12 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
 // a CTA-wide window indexed by the low bits of its dst address: later chunks read recent output from the window, the
 // chunk commits as soon as its slice is complete, and the copy to dst happens after the commit, off the chain.
 //
-// Validity: the window holds the output of the current block from `lo_rel` (chunk-relative, <= 0) on: the block start,
-// or WIN_REACH bytes back.  Older bytes are read from dst: bytes before the block were published by a CTA barrier, bytes
-// more than WIN_REACH back were flushed at least 15 chunks ago by a warp that has since passed a fence and a commit
-// which this warp has observed.  A block with a chunk longer than the tile does not use the window (k_exec_big falls
-// back to exec_chunk_tile for it), so consecutive in-flight slices never alias.
+// Validity: the window holds the output of the current run of window chunks (a run starts at a block, at a batch of
+// chunks, or after a chunk that was too long for a slice) from `lo_rel` (chunk-relative, <= 0) on: the start of the run,
+// or BIG_WIN_REACH bytes back.  Older bytes are read from dst: bytes before the run were published by a CTA barrier;
+// bytes more than BIG_WIN_REACH (> 7 slices) back were flushed at least eight chunks ago by a warp that has since passed
+// a fence and a commit, which this warp observed when it committed its own previous chunk.  All slices in flight lie
+// within BIG_WARPS consecutive slices of at most EXEC_TILE bytes, so they never alias in the window.
 constexpr uint32_t BIG_WIN = 16384, BIG_WIN_MASK = BIG_WIN - 1;
 // How far below a chunk's start the window is trusted: the other warps may be building the next BIG_WARPS - 1 chunks, whose
 // slices must not alias what this one reads.  (BIG_WARPS_MAX bounds CZB_BIG_WARPS.)
