@@ -249,10 +249,14 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
 // a fence and a commit, which this warp observed when it committed its own previous chunk.  All slices in flight lie
 // within BIG_WARPS consecutive slices of at most EXEC_TILE bytes, so they never alias in the window.
 constexpr uint32_t BIG_WIN = 16384, BIG_WIN_MASK = BIG_WIN - 1;
-// How far below a chunk's start the window is trusted: the other warps may be building the next BIG_WARPS - 1 chunks, whose
-// slices must not alias what this one reads.  (BIG_WARPS_MAX bounds CZB_BIG_WARPS.)
-constexpr int BIG_WARPS_MAX = 8;
-constexpr int BIG_WIN_REACH = (int)BIG_WIN - 64 - BIG_WARPS_MAX * (int)EXEC_TILE;
+// How far below a chunk's start the window is trusted.  Upper bound: the other warps may be building the next
+// BIG_WARPS - 1 chunks, whose slices must not alias what this one reads.  Lower bound: what is read from dst instead must
+// be visible, i.e. lie at least 2 * BIG_WARPS - 1 slices back (the warp that flushed it has committed its next chunk, and
+// this warp has seen that commit, before this warp's previous chunk committed; 2 * BIG_WARPS back it is this warp's own).
+constexpr int BIG_WARPS_MAX = 4;
+constexpr int BIG_WIN_REACH = 8128;
+static_assert(BIG_WIN_REACH <= (int)BIG_WIN - 64 - BIG_WARPS_MAX * (int)EXEC_TILE, "slices in flight must not alias the trusted part of the window");
+static_assert(BIG_WIN_REACH >= (2 * BIG_WARPS_MAX - 1) * (int)EXEC_TILE, "bytes read from dst must have been flushed before a commit this warp has seen");
 
 struct WinView {
     uint8_t* win;     // BIG_WIN bytes of shared memory, 16-byte aligned
@@ -622,7 +626,7 @@ constexpr bool BIG_USE_WIN = CZB_BIG_WIN != 0;
 #endif
 constexpr unsigned BIG_POLL_NS = CZB_BIG_POLL_NS;
 #ifndef CZB_BIG_WARPS
-#define CZB_BIG_WARPS 4  // swept 4/8/16: literal-heavy 1 MiB frames 398/367/346 GB/s, 17 MiB long-window frames 15.9/16.5/15.4 GB/s
+#define CZB_BIG_WARPS 4  // at most BIG_WARPS_MAX (window reach); swept 4/8/16 before the window: literal-heavy 1 MiB frames 398/367/346 GB/s, 17 MiB long-window frames 15.9/16.5/15.4 GB/s
 #endif
 constexpr int BIG_WARPS = CZB_BIG_WARPS;
 #ifndef CZB_BIG_MIN_CTAS
