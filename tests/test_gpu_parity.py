@@ -242,6 +242,20 @@ def test_giant_sequences_through_the_cta_per_frame_executor(monkeypatch):
         assert res[k].checksum_calculated == res[k].checksum_from_data
 
 
+def test_large_frames_inside_a_large_batch_of_small_ones():
+    """More frames than k_exec_big has resident CTAs: only the frames well above the mean go to it (share rule), the rest
+    to k_exec, side by side on two streams; every output is checked."""
+    cz = W.Compressor()
+    small = [W.synth_text(4096, 1000 + i) for i in range(1200)]
+    large = [W.synth_text(512 * 1024, 5000 + i) for i in range(3)]
+    origs = small[:600] + large[:1] + small[600:] + large[1:]
+    frames = [cz.compress(o) for o in origs]
+    outs, res = gpu_decode(frames, [len(o) for o in origs])
+    for k, o in enumerate(origs):
+        assert res[k].status == 0 and outs[k] == o, k
+        assert res[k].checksum_calculated == res[k].checksum_from_data, k
+
+
 def test_empty_and_tiny_frames(corpus):
     cz = W.Compressor()
     origs = [b"", b"a", b"ab" * 3, b"\x00" * 70000, bytes(range(256)) * 3]
