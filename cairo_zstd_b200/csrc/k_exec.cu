@@ -21,6 +21,7 @@
 // HBM traffic per frame: literals + 8 B/sequence in, decoded bytes out; match sources are recent output (L1/L2 when the
 // in-flight working set allows, DRAM otherwise: profiles/r01_final_ncu_summary.md).
 #include <cstdio>
+#include <cstdlib>
 
 #include "czb_internal.cuh"
 
@@ -982,6 +983,7 @@ void launch_exec(const LaunchCtx& lc, const ExecSide& side, const czb_frame_desc
 }
 
 int setup_exec_attributes() {
+    if (const char* e = getenv("CZB_EXEC_CARVEOUT")) cudaFuncSetAttribute(k_exec, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e));  // tuning knob (percent)
     return (int)cudaFuncSetAttribute(k_exec_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BigSmem));
 }
 
