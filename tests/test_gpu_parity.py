@@ -299,8 +299,10 @@ def test_truncations_and_bit_flips_match_oracle_status(corpus):
         if (st == 0) != (res[k].status == 0) or (st == 0 and outs[k] != want):
             mism.append((k, czb.status_name(st), czb.status_name(res[k].status)))
     assert not mism, mism[:10]
-    same_code = sum(1 for k, f in enumerate(frames) if O.decode_frame(f, dst_cap=caps[k])[0] == res[k].status)
-    assert same_code >= 0.9 * len(frames), f"only {same_code}/{len(frames)} status codes identical"
+    # leaf status codes are identical, except for the enumerated limit of this build (CZS_UNSUPPORTED = 103, see tests/test_gpu_fuzz.py)
+    diff = [(k, czb.status_name(O.decode_frame(f, dst_cap=caps[k])[0]), czb.status_name(res[k].status)) for k, f in enumerate(frames)
+            if O.decode_frame(f, dst_cap=caps[k])[0] != res[k].status and res[k].status != 103]
+    assert not diff, diff[:10]
 
 
 def test_header_level_errors_in_batch(corpus):
