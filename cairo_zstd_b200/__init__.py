@@ -7,6 +7,7 @@ the CUDA library (or without a GPU) every decode call raises.
 """
 from .api import (  # noqa: F401
     Context,
+    MultiContext,
     CzbError,
     FrameDesc,
     FrameResult,
@@ -14,6 +15,8 @@ from .api import (  # noqa: F401
     find_frame_end,
     frame_header_info,
     load_library,
+    partition_frames,
+    split_frames,
     status_name,
 )
 from .frame_decoder import (  # noqa: F401

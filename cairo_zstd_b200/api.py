@@ -33,6 +33,16 @@ class FrameHeaderInfo(C.Structure):
     ]
 
 
+class FrameSpan(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("length", C.c_uint64), ("content_size", C.c_uint64), ("window_size", C.c_uint64),
+                ("fcs_present", C.c_int32), ("has_checksum_flag", C.c_int32)]
+
+
+class ShardStat(C.Structure):
+    _fields_ = [("device", C.c_int32), ("pad", C.c_uint32), ("frames", C.c_uint64), ("bytes_in", C.c_uint64),
+                ("bytes_out", C.c_uint64), ("ms", C.c_double)]
+
+
 class DebugBlock(C.Structure):
     _fields_ = [
         ("frame", C.c_uint32), ("block_type", C.c_uint8), ("lit_type", C.c_uint8), ("n_streams", C.c_uint8), ("modes", C.c_uint8),
@@ -67,6 +77,8 @@ EXPORTS = [
     "czb_fd_get_calculated_checksum", "czb_fd_bytes_read_from_source", "czb_fd_is_finished", "czb_fd_blocks_decoded",
     "czb_debug_last_wave_counts", "czb_debug_copy_blocks", "czb_debug_copy_literals", "czb_debug_copy_sequences",
     "czb_kernel_launches", "czb_profile_enable", "czb_profile_collect", "czs_status_name",
+    "czb_split_frames_host", "czb_split_frames_device", "czb_frame_sizes_device", "czb_frame_sizes_host",
+    "czb_partition_frames", "czb_multi_create", "czb_multi_destroy", "czb_decode_batch_multi", "czb_multi_last_error",
 ]
 
 _lib = None
@@ -120,6 +132,16 @@ def load_library():
     L.czb_kernel_launches.restype = u64
     L.czb_profile_enable.argtypes = [vp, C.c_int]
     L.czb_profile_collect.argtypes = [vp, P(C.c_double), P(u64)]
+    L.czb_split_frames_host.argtypes = [C.c_char_p, u64, P(FrameSpan), u64, P(u64), P(u64), P(u64)]
+    L.czb_split_frames_device.argtypes = [vp, vp, u64, vp, u64, vp, vp]
+    L.czb_frame_sizes_device.argtypes = [vp, vp, vp, u64, vp]
+    L.czb_frame_sizes_host.argtypes = [vp, P(FrameDesc), P(FrameResult), u64]
+    L.czb_partition_frames.argtypes = [P(u64), u64, u32, P(u32), P(u64)]
+    L.czb_multi_create.argtypes = [P(C.c_int), C.c_int, u64, P(vp)]
+    L.czb_multi_destroy.argtypes = [vp]
+    L.czb_decode_batch_multi.argtypes = [vp, P(FrameDesc), P(FrameResult), u64, u32, P(ShardStat)]
+    L.czb_multi_last_error.argtypes = [vp, C.c_int]
+    L.czb_multi_last_error.restype = C.c_char_p
     L.czs_status_name.argtypes = [C.c_int]
     L.czs_status_name.restype = C.c_char_p
     _lib = L
@@ -136,6 +158,70 @@ def find_frame_end(data: bytes):
     n = C.c_uint64()
     st = load_library().czb_find_frame_end_host(data, len(data), C.byref(n))
     return st, n.value
+
+
+def split_frames(buf: bytes, cap: int = None):
+    """czb_split_frames_host: returns (status, [FrameSpan], n_skipped, consumed)."""
+    L = load_library()
+    cap = cap if cap is not None else max(1, len(buf) // 9 + 1)
+    spans = (FrameSpan * cap)()
+    n, sk, used = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    st = L.czb_split_frames_host(buf, len(buf), spans, cap, C.byref(n), C.byref(sk), C.byref(used))
+    return st, [spans[i] for i in range(n.value)], sk.value, used.value
+
+
+def partition_frames(costs, n_shards: int):
+    """czb_partition_frames: greedy largest-first; returns (shard_of list, shard_load list)."""
+    L = load_library()
+    n = len(costs)
+    c = (C.c_uint64 * max(n, 1))(*[int(x) for x in costs])
+    so = (C.c_uint32 * max(n, 1))()
+    load = (C.c_uint64 * n_shards)()
+    rc = L.czb_partition_frames(c, n, n_shards, so, load)
+    if rc != 0:
+        raise CzbError(status_name(rc))
+    return list(so[:n]), list(load)
+
+
+class MultiContext:
+    """czb_multi: one host batch decoded over several GPUs of this process (czb_decode_batch_multi)."""
+
+    def __init__(self, devices, workspace_budget_bytes: int = 0):
+        self._L = load_library()
+        h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        rc = self._L.czb_multi_create(arr, len(devices), workspace_budget_bytes, C.byref(h))
+        if rc != 0:
+            raise CzbError(f"czb_multi_create failed: {status_name(rc)}")
+        self._h, self.devices = h, list(devices)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.czb_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode_batch(self, frames, dst_caps, flags: int = 0):
+        n = len(frames)
+        descs = (FrameDesc * n)()
+        results = (FrameResult * n)()
+        stats = (ShardStat * len(self.devices))()
+        keep = []
+        for i, (f, cap) in enumerate(zip(frames, dst_caps)):
+            sb = C.create_string_buffer(f, len(f)) if len(f) else C.create_string_buffer(1)
+            db = C.create_string_buffer(max(int(cap), 1))
+            keep.append((sb, db))
+            descs[i].src, descs[i].src_len, descs[i].dst, descs[i].dst_cap = C.addressof(sb), len(f), C.addressof(db), int(cap)
+        rc = self._L.czb_decode_batch_multi(self._h, descs, results, n, flags, stats)
+        if rc != 0:
+            raise CzbError(status_name(rc))
+        outs = [keep[i][1].raw[: results[i].bytes_written] if results[i].status == 0 else None for i in range(n)]
+        return outs, results, list(stats)
 
 
 class Context:
@@ -206,7 +292,20 @@ class Context:
         self._check(self._L.czb_decode_batch_host_packed(self._h, src_base, so, dst_base, do, results_ptr, n, flags))
 
     # ---- per-kernel timing ----
-    KERNEL_CLASSES = ["scan", "fill", "huff", "fse", "exec", "xxh64", "header_results", "other"]
+    KERNEL_CLASSES = ["scan", "fill", "huff", "fse", "exec", "xxh64", "header_results", "frame_sizes"]
+
+    def frame_sizes(self, frames):
+        """czb_frame_sizes_host: exact decoded size of every frame without executing it."""
+        n = len(frames)
+        descs = (FrameDesc * n)()
+        results = (FrameResult * n)()
+        keep = []
+        for i, f in enumerate(frames):
+            sb = C.create_string_buffer(f, len(f)) if len(f) else C.create_string_buffer(1)
+            keep.append(sb)
+            descs[i].src, descs[i].src_len = C.addressof(sb), len(f)
+        self._check(self._L.czb_frame_sizes_host(self._h, descs, results, n))
+        return results
 
     def profile_enable(self, on=True):
         self._check(self._L.czb_profile_enable(self._h, 1 if on else 0))

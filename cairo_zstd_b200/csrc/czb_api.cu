@@ -6,6 +6,8 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "czb_host.h"
@@ -52,6 +54,7 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     ctx->budget = budget ? budget : (12ull << 30);
     ctx->wave_frames = 131072;
     if (const char* e = getenv("CZB_WAVE_FRAMES")) ctx->wave_frames = (uint64_t)atoll(e) > 128 ? (uint64_t)atoll(e) : 128;  // tuning knobs
+    ctx->wave_frames = (ctx->wave_frames + 127) / 128 * 128;  // k_scan_frames / k_fill_blocks: a warp or CTA never straddles two waves
     if (const char* e = getenv("CZB_BUDGET_GB")) ctx->budget = (uint64_t)atoll(e) << 30;
     // Wave pipelining over two streams is opt-in (CZB_OVERLAP=1): measured on B200 it gains ~1 % because the
     // entropy kernels and k_exec contend for the same issue slots and registers, and it makes the per-kernel
@@ -59,7 +62,7 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     ctx->no_overlap = getenv("CZB_OVERLAP") == nullptr;
     if (const char* e = getenv("CZB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (uint64_t)atoll(e) << 20;  // measurement aid: run every kernel alone
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
-    if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0 || setup_exec_attributes() != 0) { delete ctx; return CZS_CUDA_ERROR; }
+    if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0 || setup_exec_attributes() != 0) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
     // frames whose compressed size is at least 2^big_cls bytes get a whole CTA in sequence execution (k_exec_big)
     // and whose sequences are sparse (at least big_seq_bytes compressed bytes per sequence; 0 = any).  Knobs for tests.
     if (const char* e = getenv("CZB_BIG_CLS")) ctx->big_cls = atoi(e);
@@ -70,27 +73,33 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     {
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        ctx->sm_count = sms;
         ctx->big_resident = 7 * sms;  // k_exec_big CTAs that fit the machine at once (72 registers x 128 threads)
     }
     // Planning read-back buffer: host memory mapped into the device address space.  A kernel writes the
     // per-wave totals straight into it, so the read-back never queues behind a large device-to-host
     // copy on the copy engine (that serialised decode behind the previous chunk's output transfer).
     if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->totals_h), sizeof(WaveTotals) * kMaxWaves, cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->totals_h_dev), ctx->totals_h, 0) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+        cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->totals_h_dev), ctx->totals_h, 0) != cudaSuccess) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
     if (cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->exec_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+        cudaStreamCreateWithFlags(&ctx->exec_stream, cudaStreamNonBlocking) != cudaSuccess) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
     for (int s = 0; s < 2; s++)
         if (cudaEventCreateWithFlags(&ctx->ev_entropy[s], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_exec[s], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
-    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+            cudaEventCreateWithFlags(&ctx->ev_exec[s], cudaEventDisableTiming) != cudaSuccess) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_scratch_free, cudaEventDisableTiming) != cudaSuccess) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
+    for (int s = 0; s < czb_context::kHostSlots; s++)
+        if (cudaEventCreateWithFlags(&ctx->ev_in[s], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_dec[s], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_out[s], cudaEventDisableTiming) != cudaSuccess) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
     {
         int lo = 0, hi = 0;  // k_exec_big's CTAs first: the largest frames are the long pole of a wave
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&ctx->big_stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_big_fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_big_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
+            cudaEventCreateWithFlags(&ctx->ev_big_join, cudaEventDisableTiming) != cudaSuccess) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
     }
     *out = ctx;
     return CZS_OK;
@@ -109,6 +118,12 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
         if (ctx->ev_exec[s]) cudaEventDestroy(ctx->ev_exec[s]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_scratch_free) cudaEventDestroy(ctx->ev_scratch_free);
+    for (int s = 0; s < czb_context::kHostSlots; s++) {
+        if (ctx->ev_in[s]) cudaEventDestroy(ctx->ev_in[s]);
+        if (ctx->ev_dec[s]) cudaEventDestroy(ctx->ev_dec[s]);
+        if (ctx->ev_out[s]) cudaEventDestroy(ctx->ev_out[s]);
+    }
     if (ctx->ev_big_fork) cudaEventDestroy(ctx->ev_big_fork);
     if (ctx->ev_big_join) cudaEventDestroy(ctx->ev_big_join);
     if (ctx->big_stream) cudaStreamDestroy(ctx->big_stream);
@@ -161,6 +176,8 @@ static uint64_t wave_scratch_bytes(const WaveTotals& t) {
     return t.n_blocks * sizeof(BlockDesc) + t.lit_bytes + t.n_seq * sizeof(Seq) + (t.n_huf + t.n_fse) * 4 + t.n_huf * (sizeof(HufRec) + 8);
 }
 
+constexpr uint32_t kFlagSizesOnly = 0x80000000u;  // internal: scan + block walk + k_fse, then k_frame_sizes (czb_frame_sizes_*)
+
 // The hot path.  descs/results are device arrays.
 extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
                                        uint32_t flags, void* stream_v) {
@@ -171,6 +188,9 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
     cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
     LaunchCtx lc{stream, &ctx->launches};
     int rc;
+    // The per-context scratch (infos, totals, counters, blocks, literal and sequence scratch, work lists) is reused by
+    // every call: a call on another stream must not start overwriting it while the previous call's kernels still read it.
+    if (ctx->scratch_in_use) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_scratch_free, 0));
     if ((rc = ensure(ctx, ctx->infos, n))) return rc;
     if ((rc = ensure(ctx, ctx->totals_d, kMaxWaves))) return rc;
 
@@ -245,14 +265,15 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
         { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0); }
-        { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p, ctx->huf_recs[s].p, ctx->huf_cls0[s].p, ctx->huf_cls1[s].p); }
+        if (!(flags & kFlagSizesOnly)) { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p, ctx->huf_recs[s].p, ctx->huf_cls0[s].p, ctx->huf_cls1[s].p); }
         { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks[s].p, ctx->fse_items[s].p, ctx->counters[s].p, (uint32_t)t.n_fse, ctx->seq[s].p); }
         if (overlap) {
             CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
-        { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join}, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
-        if (flags & CZB_FLAG_VERIFY_CHECKSUM) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
+        if (flags & kFlagSizesOnly) { ProfScope ps(ctx, xs, 7); launch_frame_sizes(lx, ctx->infos.p, first, count, ctx->blocks[s].p, results); }
+        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        if ((flags & CZB_FLAG_VERIFY_CHECKSUM) && !(flags & kFlagSizesOnly)) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;
     }
@@ -260,8 +281,14 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 1) & 1], 0));
         if (n_waves > 1) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 2) & 1], 0));
     }
+    CZB_CUDA(ctx, cudaEventRecord(ctx->ev_scratch_free, stream));  // after the join: every kernel of this call is ordered before it
+    ctx->scratch_in_use = true;
     CZB_CUDA(ctx, cudaGetLastError());
     return CZS_OK;
+}
+
+extern "C" int czb_frame_sizes_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n, void* stream_v) {
+    return czb_decode_batch_device(ctx, descs, results, n, kFlagSizesOnly, stream_v);
 }
 
 // ---- host-pointer forms ---------------------------------------------------------------------
@@ -356,12 +383,7 @@ extern "C" int czb_decode_batch_host_packed(czb_context* ctx, const uint8_t* src
     if ((rc = ensure(ctx, ctx->h_descs, NS * max_frames))) return rc;
     if ((rc = ensure(ctx, ctx->h_results, NS * max_frames))) return rc;
     if ((rc = ensure_pinned(ctx, ctx->pin_b, ctx->pin_b_cap, NS * max_frames * sizeof(czb_frame_desc)))) return rc;
-    cudaEvent_t ev_in[NS], ev_dec[NS], ev_out[NS];
-    for (int s = 0; s < NS; s++) {
-        CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
-        CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_dec[s], cudaEventDisableTiming));
-        CZB_CUDA(ctx, cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming));
-    }
+    cudaEvent_t* ev_in = ctx->ev_in; cudaEvent_t* ev_dec = ctx->ev_dec; cudaEvent_t* ev_out = ctx->ev_out;  // owned by the context: nothing to leak on an early return
     const bool dbg = getenv("CZB_E2E_DEBUG") != nullptr;
     std::vector<cudaEvent_t> tev;  // debug: 6 timing events per chunk (h2d begin/end, decode begin/end, d2h begin/end)
     cudaEvent_t t0ev = nullptr;
@@ -429,8 +451,143 @@ extern "C" int czb_decode_batch_host_packed(czb_context* ctx, const uint8_t* src
         cudaEventDestroy(t0ev);
     }
     CZB_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
-    for (int s = 0; s < NS; s++) { cudaEventDestroy(ev_in[s]); cudaEventDestroy(ev_dec[s]); cudaEventDestroy(ev_out[s]); }
     return CZS_OK;
+}
+
+extern "C" int czb_frame_sizes_host(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n) {
+    if (!ctx || (n && (!descs || !results))) return CZS_BAD_ARGUMENT;
+    if (n == 0) return CZS_OK;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint64_t> soff(n + 1);
+    uint64_t stot = 0;
+    for (uint64_t i = 0; i < n; i++) { soff[i] = stot; stot += (descs[i].src_len + 15) & ~15ull; }
+    int rc;
+    if ((rc = ensure_pinned(ctx, ctx->pin_a, ctx->pin_a_cap, stot + 16))) return rc;
+    if ((rc = ensure_pinned(ctx, ctx->pin_b, ctx->pin_b_cap, std::max<uint64_t>(n * sizeof(czb_frame_desc), n * sizeof(czb_frame_result))))) return rc;
+    if ((rc = ensure(ctx, ctx->h_src[0], stot + 16))) return rc;
+    if ((rc = ensure(ctx, ctx->h_descs, n))) return rc;
+    if ((rc = ensure(ctx, ctx->h_results, n))) return rc;
+    czb_frame_desc* hd = reinterpret_cast<czb_frame_desc*>(ctx->pin_b);
+    for (uint64_t i = 0; i < n; i++) {
+        if (descs[i].src_len) memcpy(ctx->pin_a + soff[i], descs[i].src, descs[i].src_len);
+        hd[i].src = ctx->h_src[0].p + soff[i]; hd[i].src_len = descs[i].src_len; hd[i].dst = nullptr; hd[i].dst_cap = 0;
+    }
+    cudaStream_t st = ctx->compute;
+    CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_src[0].p, ctx->pin_a, stot, cudaMemcpyHostToDevice, st));
+    CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_descs.p, hd, n * sizeof(czb_frame_desc), cudaMemcpyHostToDevice, st));
+    if ((rc = czb_decode_batch_device(ctx, ctx->h_descs.p, ctx->h_results.p, n, kFlagSizesOnly, st))) return rc;
+    CZB_CUDA(ctx, cudaMemcpyAsync(ctx->pin_b, ctx->h_results.p, n * sizeof(czb_frame_result), cudaMemcpyDeviceToHost, st));
+    CZB_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(results, ctx->pin_b, n * sizeof(czb_frame_result));
+    return CZS_OK;
+}
+
+// ---- batch splitter ------------------------------------------------
+extern "C" int czb_split_frames_host(const uint8_t* buf, uint64_t len, czb_frame_span* spans, uint64_t cap, uint64_t* n_frames,
+                                     uint64_t* n_skipped, uint64_t* consumed) {
+    if ((!buf && len) || (!spans && cap) || !n_frames) return CZS_BAD_ARGUMENT;
+    uint64_t n = 0, sk = 0, pos = 0;
+    const int32_t st = split_frames_walk(buf, len, spans, cap, n, sk, pos);
+    *n_frames = n;
+    if (n_skipped) *n_skipped = sk;
+    if (consumed) *consumed = pos;
+    return st;
+}
+extern "C" int czb_split_frames_device(czb_context* ctx, const uint8_t* buf, uint64_t len, czb_frame_span* spans, uint64_t cap,
+                                       uint64_t* counts, void* stream_v) {
+    if (!ctx || (!buf && len) || (!spans && cap) || !counts) return CZS_BAD_ARGUMENT;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    LaunchCtx lc{static_cast<cudaStream_t>(stream_v), &ctx->launches};
+    launch_split_frames(lc, buf, len, spans, cap, reinterpret_cast<unsigned long long*>(counts));
+    CZB_CUDA(ctx, cudaGetLastError());
+    return CZS_OK;
+}
+
+// ---- one host batch over several GPUs --------------------------------------
+extern "C" int czb_partition_frames(const uint64_t* cost, uint64_t n, uint32_t n_shards, uint32_t* shard_of, uint64_t* shard_load) {
+    if (!n_shards || (n && (!cost || !shard_of))) return CZS_BAD_ARGUMENT;
+    std::vector<uint64_t> order(n), load(n_shards, 0);
+    for (uint64_t i = 0; i < n; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return cost[a] != cost[b] ? cost[a] > cost[b] : a < b; });
+    // largest first onto the least loaded shard (ties: lowest shard index); a heap keeps it O(n log shards)
+    using Slot = std::pair<uint64_t, uint32_t>;
+    std::vector<Slot> heap;
+    for (uint32_t sI = 0; sI < n_shards; sI++) heap.push_back({0, sI});
+    auto worse = [](const Slot& a, const Slot& b) { return a.first != b.first ? a.first > b.first : a.second > b.second; };
+    std::make_heap(heap.begin(), heap.end(), worse);
+    for (uint64_t k = 0; k < n; k++) {
+        std::pop_heap(heap.begin(), heap.end(), worse);
+        Slot& sl = heap.back();
+        shard_of[order[k]] = sl.second;
+        sl.first += cost[order[k]]; load[sl.second] = sl.first;
+        std::push_heap(heap.begin(), heap.end(), worse);
+    }
+    if (shard_load) for (uint32_t sI = 0; sI < n_shards; sI++) shard_load[sI] = load[sI];
+    return CZS_OK;
+}
+
+struct czb_multi {
+    std::vector<czb_context*> ctxs;
+    std::vector<int> devices;
+};
+extern "C" int czb_multi_create(const int* devices, int n_devices, uint64_t budget, czb_multi** out) {
+    if (!out || !devices || n_devices <= 0) return CZS_BAD_ARGUMENT;
+    *out = nullptr;
+    czb_multi* m = new czb_multi();
+    for (int d = 0; d < n_devices; d++) {
+        czb_context* c = nullptr;
+        const int rc = czb_context_create(devices[d], budget, &c);
+        if (rc != CZS_OK) { czb_multi_destroy(m); return rc; }
+        m->ctxs.push_back(c); m->devices.push_back(devices[d]);
+    }
+    *out = m;
+    return CZS_OK;
+}
+extern "C" void czb_multi_destroy(czb_multi* m) {
+    if (!m) return;
+    for (auto c : m->ctxs) czb_context_destroy(c);
+    delete m;
+}
+extern "C" int czb_decode_batch_multi(czb_multi* m, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n, uint32_t flags,
+                                      czb_shard_stat* stats) {
+    if (!m || (n && (!descs || !results))) return CZS_BAD_ARGUMENT;
+    const uint32_t S = (uint32_t)m->ctxs.size();
+    std::vector<uint64_t> cost(n);
+    for (uint64_t i = 0; i < n; i++) cost[i] = descs[i].src_len + descs[i].dst_cap;
+    std::vector<uint32_t> shard_of(n);
+    int rc = czb_partition_frames(cost.data(), n, S, shard_of.data(), nullptr);
+    if (rc != CZS_OK) return rc;
+    std::vector<std::vector<uint64_t>> idx(S);
+    for (uint64_t i = 0; i < n; i++) idx[shard_of[i]].push_back(i);
+    std::vector<int> rcs(S, CZS_OK);
+    std::vector<double> ms(S, 0.0);
+    std::vector<std::thread> th;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    for (uint32_t sI = 0; sI < S; sI++) {
+        th.emplace_back([&, sI]() {  // one host thread per device: a context is not shareable, different contexts are
+            const double t0 = now_ms();
+            const std::vector<uint64_t>& ix = idx[sI];
+            std::vector<czb_frame_desc> d(ix.size());
+            std::vector<czb_frame_result> r(ix.size());
+            for (size_t k = 0; k < ix.size(); k++) d[k] = descs[ix[k]];
+            rcs[sI] = czb_decode_batch_host(m->ctxs[sI], d.data(), r.data(), ix.size(), flags);
+            if (rcs[sI] == CZS_OK) for (size_t k = 0; k < ix.size(); k++) results[ix[k]] = r[k];  // disjoint slots: the only "gather"
+            ms[sI] = now_ms() - t0;
+        });
+    }
+    for (auto& t : th) t.join();
+    if (stats) {
+        for (uint32_t sI = 0; sI < S; sI++) {
+            czb_shard_stat& st = stats[sI];
+            st.device = m->devices[sI]; st.pad = 0; st.frames = idx[sI].size(); st.bytes_in = 0; st.bytes_out = 0; st.ms = ms[sI];
+            for (uint64_t i : idx[sI]) { st.bytes_in += descs[i].src_len; if (rcs[sI] == CZS_OK && results[i].status == CZS_OK) st.bytes_out += results[i].bytes_written; }
+        }
+    }
+    for (uint32_t sI = 0; sI < S; sI++) if (rcs[sI] != CZS_OK) return rcs[sI];
+    return CZS_OK;
+}
+extern "C" const char* czb_multi_last_error(const czb_multi* m, int shard) {
+    return (m && shard >= 0 && (size_t)shard < m->ctxs.size()) ? czb_last_error(m->ctxs[shard]) : "bad shard";
 }
 
 // ---- header pre-pass (CPU only) ---------------------------------------------------------------

@@ -38,6 +38,9 @@ struct czb_context {
     DevBuf<czb::Seq> seq[2];
     cudaStream_t exec_stream = nullptr;
     cudaEvent_t ev_entropy[2] = {nullptr, nullptr}, ev_exec[2] = {nullptr, nullptr}, ev_fork = nullptr;
+    cudaEvent_t ev_scratch_free = nullptr;  // recorded at the end of every batch call: the next call (any stream) waits on it
+    bool scratch_in_use = false;
+    int sm_count = 148;
     int last_set = 0;
     bool no_overlap = false;
     int big_cls = 19;           // frames of >= 2^big_cls compressed bytes are executed by one CTA each (k_exec_big); 32 = never
@@ -56,6 +59,7 @@ struct czb_context {
     uint8_t* pin_a = nullptr; uint64_t pin_a_cap = 0;
     uint8_t* pin_b = nullptr; uint64_t pin_b_cap = 0;
     cudaStream_t copy_in = nullptr, copy_out = nullptr, compute = nullptr;
+    cudaEvent_t ev_in[kHostSlots] = {}, ev_dec[kHostSlots] = {}, ev_out[kHostSlots] = {};  // packed host path pipeline
 
     // per-kernel profiling
     bool profiling = false;

@@ -148,4 +148,55 @@ __host__ __device__ inline void parse_block_at(const uint8_t* src, uint64_t len,
     b.seq_hdr = br + 1;
 }
 
+// End of the zstd frame that starts at src[0]: header, blocks up to the last one, checksum trailer.
+__host__ __device__ inline int32_t frame_end_walk(const uint8_t* src, uint64_t len, const FrameHeader& fh, uint64_t& frame_len) {
+    uint64_t pos = fh.hdr_len;
+    for (;;) {
+        if (len - pos < 3) return CZS_PANIC_TRUNCATED;
+        const uint8_t a = src[pos];
+        const uint32_t t = (a >> 1) & 3;
+        if (t == 3) return CZS_FOUND_RESERVED_BLOCK;
+        const uint32_t size = (a >> 3) | ((uint32_t)src[pos + 1] << 5) | ((uint32_t)src[pos + 2] << 13);
+        if (size > MAX_BLOCK_SIZE) return CZS_BLOCK_SIZE_TOO_LARGE;
+        const uint32_t content = t == BT_RLE ? 1u : size;
+        if (len - pos - 3 < content) return CZS_PANIC_TRUNCATED;
+        pos += 3 + content;
+        if (a & 1) break;
+    }
+    if ((fh.descriptor >> 2) & 1) { if (len - pos < 4) return CZS_PANIC_TRUNCATED; pos += 4; }
+    frame_len = pos;
+    return CZS_OK;
+}
+
+// Walk a buffer of concatenated frames.  Skippable frames (magic 0x184D2A50..5F followed by a
+// 4-byte little-endian size, frame.cairo:160-166 reports them as SkipFrame) are stepped over and counted; every zstd frame
+// is appended to spans[] until `cap` is reached.  Stops at the end of the buffer (CZS_OK), when spans is full (CZS_OK,
+// pos < len) or at the first frame that cannot be delimited (its status; pos = where it starts).
+__host__ __device__ inline int32_t split_frames_walk(const uint8_t* buf, uint64_t len, czb_frame_span* spans, uint64_t cap,
+                                                     uint64_t& n, uint64_t& skipped, uint64_t& pos) {
+    n = 0; skipped = 0; pos = 0;
+    while (pos < len && n < cap) {
+        FrameHeader fh{};
+        const int32_t st = parse_frame_header(buf + pos, len - pos, fh);
+        if (st == CZS_SKIP_FRAME) {
+            const uint8_t* p = buf + pos + 4;
+            const uint64_t user = (uint64_t)p[0] | ((uint64_t)p[1] << 8) | ((uint64_t)p[2] << 16) | ((uint64_t)p[3] << 24);
+            if (len - pos - 8 < user) return CZS_PANIC_TRUNCATED;
+            pos += 8 + user; skipped++;
+            continue;
+        }
+        if (st != CZS_OK) return st;
+        uint64_t ws = 0, flen = 0;
+        int32_t st2 = frame_window_size(fh, false, ws);
+        if (st2 == CZS_OK) st2 = frame_end_walk(buf + pos, len - pos, fh, flen);
+        if (st2 != CZS_OK) return st2;
+        czb_frame_span sp;
+        sp.offset = pos; sp.length = flen; sp.content_size = fh.fcs; sp.window_size = ws;
+        sp.fcs_present = fh.fcs_bytes != 0; sp.has_checksum_flag = (fh.descriptor >> 2) & 1;
+        spans[n++] = sp;
+        pos += flen;
+    }
+    return CZS_OK;
+}
+
 }  // namespace czb

@@ -948,18 +948,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
 #endif
 }
 
-static int exec_persistent_ctas() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        n = sms * EXEC_CTAS_PER_SM;
-    }
-    return n;
-}
-
-void launch_exec(const LaunchCtx& lc, const ExecSide& side, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_big_cls,
+void launch_exec(const LaunchCtx& lc, const ExecSide& side, int sm_count, const czb_frame_desc* descs, const FrameInfo* infos, uint64_t first, uint64_t count, uint32_t n_big_cls,
                  uint32_t n_exec, BigRule rule, WaveCounters* counters,
                  const uint32_t* exec_order, BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch,
                  czb_frame_result* results) {
@@ -976,7 +965,8 @@ void launch_exec(const LaunchCtx& lc, const ExecSide& side, const czb_frame_desc
         ++*lc.launches;
     }
     const uint64_t want = ((uint64_t)n_exec + EXEC_WARPS - 1) / EXEC_WARPS;
-    const unsigned grid = (unsigned)(want < (uint64_t)exec_persistent_ctas() ? want : (uint64_t)exec_persistent_ctas());
+    const uint64_t persistent = (uint64_t)sm_count * EXEC_CTAS_PER_SM;  // per device: the context carries its own SM count
+    const unsigned grid = (unsigned)(want < persistent ? want : persistent);
     k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, rule, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
     ++*lc.launches;
     if (n_big_cls) cudaStreamWaitEvent(lc.stream, side.join, 0);

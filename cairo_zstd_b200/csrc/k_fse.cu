@@ -206,11 +206,13 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
     // which it did is decoded again by the exact form, which records WHICH error came first, in the reference's order
     // (two compares and selects per step: 8 % of the kernel when it was always on).
     const uint32_t h_in0 = h0, h_in1 = h1, h_in2 = h2;
+    uint32_t ml_total = 0;
     auto decode = [&](auto exact_tag) -> int32_t {
     constexpr bool EXACT = decltype(exact_tag)::value;
     int32_t st = CZS_OK;
     uint32_t trouble = 0;  // fast form: bit 31 set <=> a bad code or an over-read happened somewhere
     h0 = h_in0; h1 = h_in1; h2 = h_in2;
+    ml_total = 0;
     {
         // phase 1's scratch is dead now (the other warps have left): it becomes the lanes' bitstream rings
         RevBitsWin br;
@@ -242,9 +244,11 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             RevBitsWin::Raw64 win = br.window64_raw();
             const uint32_t dummy = (uint32_t)__cvta_generic_to_shared(sm.tmp) + FSE_SLOTS * RevBitsWin::RING + lane * 16u;
             uint32_t nbLL = fse_entry_nbits(eLL, logLL), nbML = fse_entry_nbits(eML, logML), nbOF = fse_entry_nbits(eOF, logOF);
-            auto step = [&](uint32_t i, auto more_tag, auto refill_tag) {
+            Seq quad[4];  // four records leave as two 16-byte stores: a block's slice of the scratch is 32-byte aligned (k_fill_blocks)
+            auto step = [&](uint32_t i, auto more_tag, auto refill_tag, auto quad_tag) {
                 constexpr bool MORE = decltype(more_tag)::value;
                 constexpr int REFILLS = decltype(refill_tag)::value;  // ring slots to look after in this step
+                constexpr int QUAD = decltype(quad_tag)::value;       // position inside the group of four (-1: store it alone)
                 br.step_sync();
                 const uint32_t ofc = fse_entry_sym(eOF);
                 // :235-237; codes beyond the tables give (0,255) -> TooManyBits
@@ -296,7 +300,10 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 h2 = (rep & (idx <= 1)) ? h2 : h1;
                 h1 = (rep & (idx == 0)) ? h1 : h0;
                 h0 = act;
-                __stcs(out + i, (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35));  // written once, read by a later kernel: streaming store
+                ml_total += ml;  // the block's output size is regen + sum(ml): what czb_frame_sizes_* reports without executing
+                const Seq rec = (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35);
+                if constexpr (QUAD < 0) __stcs(out + i, rec);  // written once, read by a later kernel: streaming store
+                else quad[QUAD] = rec;
                 if (MORE) {
                     lle = sm.ll_code[fse_entry_sym(eLL)]; mle = sm.ml_code[fse_entry_sym(eML)];
                     nbLL = fse_entry_nbits(eLL, logLL); nbML = fse_entry_nbits(eML, logML); nbOF = fse_entry_nbits(eOF, logOF);
@@ -308,13 +315,18 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             // Four steps consume at most 356 bits, i.e. leave at most three 16-byte chunks behind: the ring is looked after
             // once per four steps (three always-issued cp.async) instead of once per step.
             using R0 = std::integral_constant<int, 0>; using R1 = std::integral_constant<int, 1>; using R3 = std::integral_constant<int, 3>;
+            using Q0 = std::integral_constant<int, 0>; using Q1 = std::integral_constant<int, 1>; using Q2 = std::integral_constant<int, 2>;
+            using Q3 = std::integral_constant<int, 3>; using QN = std::integral_constant<int, -1>;
             uint32_t i = 0;
             for (; i + 4 < n_seq; i += 4) {
-                step(i, std::true_type{}, R0{}); step(i + 1, std::true_type{}, R0{});
-                step(i + 2, std::true_type{}, R0{}); step(i + 3, std::true_type{}, R3{});
+                step(i, std::true_type{}, R0{}, Q0{}); step(i + 1, std::true_type{}, R0{}, Q1{});
+                step(i + 2, std::true_type{}, R0{}, Q2{}); step(i + 3, std::true_type{}, R3{}, Q3{});
+                uint4* o4 = reinterpret_cast<uint4*>(out + i);
+                __stcs(o4, make_uint4((uint32_t)quad[0], (uint32_t)(quad[0] >> 32), (uint32_t)quad[1], (uint32_t)(quad[1] >> 32)));
+                __stcs(o4 + 1, make_uint4((uint32_t)quad[2], (uint32_t)(quad[2] >> 32), (uint32_t)quad[3], (uint32_t)(quad[3] >> 32)));
             }
-            for (; i + 1 < n_seq; i++) step(i, std::true_type{}, R1{});
-            step(i, std::false_type{}, R0{});
+            for (; i + 1 < n_seq; i++) step(i, std::true_type{}, R1{}, QN{});
+            step(i, std::false_type{}, R0{}, QN{});
             if (!EXACT && (trouble >> 31)) st = CZS_NOT_DECODED;  // placeholder: the exact form decides
             if (st == CZS_OK && br.rem() > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
         }
@@ -328,6 +340,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
     BlockDesc& d = blocks[sl.blk];
     d.fse_status = st;
     d.hist_out[0] = h0; d.hist_out[1] = h1; d.hist_out[2] = h2;
+    d.ml_sum = ml_total;
 }
 
 void launch_fse(const LaunchCtx& lc, const czb_frame_desc* descs, BlockDesc* blocks, const uint32_t* items,

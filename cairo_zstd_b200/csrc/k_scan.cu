@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __res
                 if (pb.hdr_status != CZS_OK) break;
                 if (pb.type == BT_COMPRESSED && pb.pre_status == CZS_OK) {
                     if (pb.lit_type >= LT_COMPRESSED) { fi.n_huf++; fi.lit_bytes += align16((uint64_t)pb.regen + 16); }
-                    if (pb.seqhdr_status == CZS_OK && pb.n_seq) { fi.n_fse++; fi.n_seq += pb.n_seq; }
+                    if (pb.seqhdr_status == CZS_OK && pb.n_seq) { fi.n_fse++; fi.n_seq += seq_slots(pb.n_seq); fi.n_seq_true += pb.n_seq; }
                 }
                 pos += 3 + pb.content;
                 if (pb.last) {
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __res
             }
             src_bytes = pos;
             fi.size_cls = size_class(pos);
-            fi.fse_cls = fi.n_fse ? size_class(fi.n_seq / fi.n_fse) : 0u;
+            fi.fse_cls = fi.n_fse ? size_class(fi.n_seq_true / fi.n_fse) : 0u;
             atomicAdd(&hist[0][fi.size_cls], 1u);
             if (fi.n_fse) atomicAdd(&hist[1][fi.fse_cls], fi.n_fse);
         }
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __res
                         }
                         d.first_in_frame = seen_seq ? 0 : 1;
                         seen_seq = true;
-                        d.seq_off = seq_base; seq_base += pb.n_seq;
+                        d.seq_off = seq_base; seq_base += seq_slots(pb.n_seq);
                         fse_items[fse_pos++] = bidx;
                     }
                 }
@@ -277,6 +277,65 @@ __global__ void k_publish_totals(const WaveTotals* __restrict__ src, WaveTotals*
     const uint64_t n_words = n_waves * (sizeof(WaveTotals) / sizeof(unsigned long long));
     if (i < n_words) reinterpret_cast<volatile unsigned long long*>(dst_host)[i] = reinterpret_cast<const unsigned long long*>(src)[i];
     __threadfence_system();
+}
+
+// Exact decoded size of every frame without executing it (51 of the 100 corpus frames carry
+// no Frame_Content_Size).  After the scan, the block walk and k_fse: a Raw/RLE block regenerates Block_Size bytes
+// (block_decoder.cairo:97-123), a Compressed block all of its literals plus every match: regen + sum(ml)
+// (sequence_execution.cairo:72-81).  Errors the literal decode or the execution would raise are not seen here.
+__global__ void __launch_bounds__(128) k_frame_sizes(const FrameInfo* __restrict__ infos, uint64_t first, uint64_t count,
+                                                      const BlockDesc* __restrict__ blocks, czb_frame_result* __restrict__ results) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const FrameInfo fi = infos[first + t];
+    if (fi.status != CZS_OK) return;  // k_header_results already reported it
+    uint64_t out = 0, bytes_read = fi.hdr_len;
+    int32_t status = CZS_OK;
+    uint32_t n_done = 0;
+    bool finished = false;
+    for (uint32_t k = 0; k < fi.n_blocks && status == CZS_OK; k++) {
+        const BlockDesc d = blocks[fi.block_base + k];
+        if (d.type == BT_ERROR) { status = d.pre_status; break; }
+        if (d.type == BT_RAW) { out += d.size; bytes_read += 3ull + d.size; }
+        else if (d.type == BT_RLE) { out += d.size; bytes_read += 4; }
+        else {
+            if (d.pre_status != CZS_OK) { status = d.pre_status; break; }
+            if (d.seqhdr_status != CZS_OK) { status = d.seqhdr_status; break; }
+            if (d.n_seq && d.fse_status != CZS_OK) { status = d.fse_status; break; }
+            out += (uint64_t)d.regen + (d.n_seq ? d.ml_sum : 0u);
+            bytes_read += 3ull + d.size;
+        }
+        n_done++;
+        if (d.last) { finished = true; if ((fi.descriptor >> 2) & 1) bytes_read += 4; }
+    }
+    czb_frame_result r;
+    r.status = status; r.blocks_decoded = n_done; r.bytes_read = bytes_read;
+    r.bytes_written = status == CZS_OK ? out : 0;
+    r.content_size = fi.fcs; r.window_size = fi.window; r.checksum_from_data = fi.checksum; r.checksum_calculated = 0;
+    r.has_checksum = fi.has_checksum;
+    r.finished = (status == CZS_OK && finished && (!((fi.descriptor >> 2) & 1) || fi.has_checksum)) ? 1 : 0;
+    results[first + t] = r;
+}
+void launch_frame_sizes(const LaunchCtx& lc, const FrameInfo* infos, uint64_t first, uint64_t count, const BlockDesc* blocks,
+                        czb_frame_result* results) {
+    if (!count) return;
+    k_frame_sizes<<<(unsigned)((count + 127) / 128), 128, 0, lc.stream>>>(infos, first, count, blocks, results);
+    ++*lc.launches;
+}
+
+// Frame-boundary walk over a concatenated buffer, one thread (each frame starts where the previous one ends, so the walk
+// is one chain of dependent loads): skippable frames are stepped over (frame.cairo:160-166), every zstd frame's end is
+// found from its block headers (block_decoder.cairo:237-278) without decoding.  counts = {frames, skipped, consumed, status}.
+__global__ void k_split_frames(const uint8_t* __restrict__ buf, uint64_t len, czb_frame_span* __restrict__ spans, uint64_t cap,
+                               unsigned long long* __restrict__ counts) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint64_t n = 0, skipped = 0, pos = 0;
+    const int32_t st = split_frames_walk(buf, len, spans, cap, n, skipped, pos);
+    counts[0] = n; counts[1] = skipped; counts[2] = pos; counts[3] = (unsigned long long)(long long)st;
+}
+void launch_split_frames(const LaunchCtx& lc, const uint8_t* buf, uint64_t len, czb_frame_span* spans, uint64_t cap, unsigned long long* counts) {
+    k_split_frames<<<1, 32, 0, lc.stream>>>(buf, len, spans, cap, counts);
+    ++*lc.launches;
 }
 
 void launch_publish_totals(const LaunchCtx& lc, const WaveTotals* totals_d, WaveTotals* totals_host_mapped, uint64_t n_waves) {

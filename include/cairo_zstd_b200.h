@@ -15,6 +15,17 @@
  *
  * Threading: a context / handle is not shareable between threads (the reference is
  * single-threaded too).  Different contexts may be used concurrently.
+ * Calls on one context may use different streams: every batch call first waits (on its stream)
+ * for the previous call's kernels, because the context's scratch is reused.
+ *
+ * Deliberate differences from the reference (all visible as statuses, see also czstd_status.h):
+ *   1. Direct 4-bit Huffman weights are read in RFC 8878 order (even index = high nibble).
+ *      src/huff0/huff0_decoder.cairo:302 reads `idx | 1 == 1`, i.e. (idx|1)==1; the reference's
+ *      own fixtures pin only the RFC behaviour.
+ *   2. CZS_UNSUPPORTED marks input the reference accepts but this build does not decode:
+ *      a Huffman-weight FSE table with accuracy log > 9 (the reference passes a limit of 100,
+ *      huff0_decoder.cairo:176; RFC 8878 allows 6) and frames whose output reaches 2^28 - 1 bytes.
+ *      It never means "malformed".
  */
 #ifndef CAIRO_ZSTD_B200_H
 #define CAIRO_ZSTD_B200_H
@@ -114,6 +125,57 @@ int czb_frame_header_info_host(const uint8_t* src, uint64_t src_len, czb_frame_h
  * *frame_len = header + blocks + checksum bytes. */
 int czb_find_frame_end_host(const uint8_t* src, uint64_t src_len, uint64_t* frame_len);
 
+/* ---- batch splitter and output sizing ------------------------ */
+/* One zstd frame found inside a buffer of concatenated frames. */
+typedef struct czb_frame_span {
+    uint64_t offset;         /* of the frame's magic number inside the buffer                    */
+    uint64_t length;         /* header + blocks + checksum trailer                               */
+    uint64_t content_size;   /* Frame_Content_Size (valid iff fcs_present), content_size() :125  */
+    uint64_t window_size;    /* FrameHeader::window_size, src/frame.cairo:106-129                */
+    int32_t fcs_present;
+    int32_t has_checksum_flag;
+} czb_frame_span;
+/* Walk `buf`: skippable frames (src/frame.cairo:160-166 reports them as SkipFrame) are stepped over and counted, every
+ * zstd frame is delimited from its block headers (src/decoding/block_decoder.cairo:237-278) without decoding and
+ * appended to spans[0..cap).  *consumed = offset where the walk stopped: the end of the buffer, the frame that did
+ * not fit spans[], or the first frame that cannot be delimited (then its czs_status is returned).
+ * Host form: CPU only, no GPU work.  Device form: buf/spans/counts are DEVICE pointers, counts = uint64[4] =
+ * {frames, skipped, consumed, status}; one thread walks (frame k+1 starts where frame k ends). */
+int czb_split_frames_host(const uint8_t* buf, uint64_t len, czb_frame_span* spans, uint64_t cap, uint64_t* n_frames,
+                          uint64_t* n_skipped, uint64_t* consumed);
+int czb_split_frames_device(czb_context* ctx, const uint8_t* buf, uint64_t len, czb_frame_span* spans, uint64_t cap,
+                            uint64_t* counts, void* stream);
+/* Exact decoded size of every frame WITHOUT executing it, for frames that carry no Frame_Content_Size: header scan,
+ * block walk and the sequence-section decode only (a Raw/RLE block regenerates Block_Size bytes, a Compressed block
+ * regenerated_size + sum of match lengths: src/decoding/sequence_execution.cairo:72-81).  descs[i].dst/dst_cap are
+ * ignored.  results[i].bytes_written = the size, .bytes_read = the frame's length, .status = the first header /
+ * sequence-section error (errors that only literal decoding or execution would raise are not seen here). */
+int czb_frame_sizes_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n_frames,
+                           void* stream);
+int czb_frame_sizes_host(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n_frames);
+
+/* ---- one host batch over several GPUs ------------------------------- */
+/* Frames are independent (DecoderScratch::reset clears everything, src/decoding/scratch.cairo:42-58), so a batch
+ * shards with no data-path collective and a frame is never split.  czb_partition_frames: greedy largest-first
+ * assignment of frames to n_shards by cost[i] (use compressed + decoded bytes), deterministic; shard_of[i] receives the
+ * shard, shard_load[s] (optional) the summed cost. */
+int czb_partition_frames(const uint64_t* cost, uint64_t n_frames, uint32_t n_shards, uint32_t* shard_of, uint64_t* shard_load);
+typedef struct czb_multi czb_multi;
+typedef struct czb_shard_stat {
+    int32_t device;
+    uint32_t pad;
+    uint64_t frames, bytes_in, bytes_out; /* this shard's frames, compressed and decoded bytes */
+    double ms;                            /* host wall clock of this device's part of the call   */
+} czb_shard_stat;
+/* One context per listed device; czb_decode_batch_multi partitions the HOST batch (same meaning of descs/results as
+ * czb_decode_batch_host) by src_len + dst_cap, runs every shard on its device from its own host thread and writes
+ * results[] in the caller's order.  stats (optional) receives n_devices entries. */
+int czb_multi_create(const int* devices, int n_devices, uint64_t workspace_budget_bytes, czb_multi** out);
+void czb_multi_destroy(czb_multi* m);
+int czb_decode_batch_multi(czb_multi* m, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n_frames,
+                           uint32_t flags, czb_shard_stat* stats);
+const char* czb_multi_last_error(const czb_multi* m, int shard);
+
 /* ---- FrameDecoder handle (1:1 mirror of src/frame_decoder.cairo) --------------------- */
 typedef struct czb_frame_decoder czb_frame_decoder;
 
@@ -167,7 +229,7 @@ int czb_debug_copy_sequences(czb_context* ctx, uint32_t* out /* 3 u32 per seq: l
 uint64_t czb_kernel_launches(const czb_context* ctx);
 
 /* Per-kernel device timing (CUDA events recorded on the launching stream around every kernel).
- * Classes: 0 scan, 1 fill, 2 huff, 3 fse, 4 exec, 5 xxh64, 6 header-results.
+ * Classes: 0 scan, 1 fill, 2 huff, 3 fse, 4 exec, 5 xxh64, 6 header-results, 7 frame-sizes.
  * czb_profile_collect synchronises on the recorded events, adds their elapsed times (ms) and
  * launch counts per class into the arrays (8 entries each) and clears the recording. */
 #define CZB_PROFILE_CLASSES 8
