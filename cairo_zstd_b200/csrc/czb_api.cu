@@ -18,6 +18,7 @@ namespace czb {
 int setup_huff_attributes();
 int setup_fse_attributes();
 int setup_exec_attributes();
+int setup_exec_flow_attributes();
 }  // namespace czb
 
 using namespace czb;
@@ -62,9 +63,10 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     ctx->no_overlap = getenv("CZB_OVERLAP") == nullptr;
     if (const char* e = getenv("CZB_HOST_CHUNK_MB")) ctx->host_chunk_bytes = (uint64_t)atoll(e) << 20;  // measurement aid: run every kernel alone
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CZS_CUDA_ERROR; }
-    if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0 || setup_exec_attributes() != 0) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
+    if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0 || setup_exec_attributes() != 0 || setup_exec_flow_attributes() != 0) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
     // frames whose compressed size is at least 2^big_cls bytes get a whole CTA in sequence execution (k_exec_big)
     // and whose sequences are sparse (at least big_seq_bytes compressed bytes per sequence; 0 = any).  Knobs for tests.
+    if (const char* e = getenv("CZB_BIG_FLOW")) ctx->big_flow = atoi(e) != 0;  // 0: the round-1 in-order executor (k_exec_big), for A/B
     if (const char* e = getenv("CZB_BIG_CLS")) ctx->big_cls = atoi(e);
     if (const char* e = getenv("CZB_BIG_SEQ_BYTES")) ctx->big_seq_bytes = atoi(e);
     if (const char* e = getenv("CZB_SHARE_CLS")) ctx->share_cls = atoi(e);
@@ -272,7 +274,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
         if (flags & kFlagSizesOnly) { ProfScope ps(ctx, xs, 7); launch_frame_sizes(lx, ctx->infos.p, first, count, ctx->blocks[s].p, results); }
-        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join, ctx->big_flow}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if ((flags & CZB_FLAG_VERIFY_CHECKSUM) && !(flags & kFlagSizesOnly)) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;

@@ -48,6 +48,7 @@ struct czb_context {
     int share_cls = 15;         // ... or, from 2^share_cls compressed bytes on, if they hold at least 1/big_share of their wave's
     int big_resident = 1036;    //     (with more frames than resident CTAs in the wave: and at least 1.5x the mean frame)
     int big_share = 8192;       //     compressed bytes: one warp would still be on such a frame when the others have finished
+    bool big_flow = true;       // CTA-per-frame executor: k_exec_flow (data-flow order) or k_exec_big (in-order commit)
     cudaStream_t big_stream = nullptr;  // k_exec_big runs beside k_exec (its CTAs are latency bound and leave most issue slots free)
     cudaEvent_t ev_big_fork = nullptr, ev_big_join = nullptr;
 
