@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=131072)
     ap.add_argument("--verify-checksum", action="store_true", help="include the XXH64 kernel in the timed region")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config3/4/5 and config5_sharded keys")
+    ap.add_argument("--no-link-ceiling", action="store_true", help="skip the raw H2D+D2H ceiling of the e2e record")
     return ap.parse_args()
 
 
@@ -313,6 +315,15 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_e2e:
         e2e = run_e2e(args, ctx, frames, origs, flens, n, dev, dist, torch)
 
+    # ---- the other BASELINE configs (extra keys; config 2 above is the bench line) ----
+    del src_all, dst_all, descs, results
+    torch.cuda.empty_cache()
+    others, sharded = {}, None
+    if not args.no_other_configs:
+        if world == 1:
+            others = other_configs(args, ctx, torch, dev, peak)
+        sharded = config5_sharded(args, ctx, torch, dev, dist, rank, world)
+
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -337,6 +348,9 @@ def run_b200(args, rank, world, local_rank):
                               "note": "rank 0, one pass (after one warm-up pass) with CZB_FLAG_VERIFY_CHECKSUM (XXH64 of every output on the device, "
                                       "compared with the frame trailer); SURVEY 8 row f1, outside the headline's timed region"},
         }
+        line.update(others)
+        if sharded is not None:
+            line["config5_sharded"] = sharded
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
@@ -345,6 +359,151 @@ def run_b200(args, rank, world, local_rank):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------
+# the other BASELINE configs as extra keys of the bench line (parity-test configs, device-timed, every frame verified)
+# --------------------------------------------------------------------------------------------
+RES_DT = np.dtype([("status", "<i4"), ("blocks", "<u4"), ("bytes_read", "<u8"), ("bytes_written", "<u8"), ("content_size", "<u8"),
+                   ("window", "<u8"), ("chk_data", "<u4"), ("chk_calc", "<u4"), ("has_chk", "<i4"), ("finished", "<i4")])
+
+
+def device_time_frames(ctx, torch, dev, frames, origs, pick, reps_of, steps=3):
+    """Device-timed decode of the frames `pick` (indices into the replicated batch: index i = rep * n0 + distinct) on this GPU.
+    The distinct set is uploaded once per replica (physical copies, different addresses).  Every output is verified: status,
+    size, and XXH64 computed on the device against the frame trailer (one extra, untimed pass).  Returns (ms, out_bytes, comp_bytes)."""
+    from cairo_zstd_b200 import api
+    n0 = len(frames)
+    flens = np.array([len(f) for f in frames], dtype=np.int64)
+    olens = np.array([len(o) for o in origs], dtype=np.int64)
+    foff = np.concatenate([[0], np.cumsum((flens + 15) & ~15)])
+    host = np.zeros(int(foff[-1]), dtype=np.uint8)
+    for i, f in enumerate(frames):
+        host[foff[i]:foff[i] + len(f)] = np.frombuffer(f, dtype=np.uint8)
+    pick = np.asarray(pick, dtype=np.int64)
+    n = int(pick.size)
+    if n == 0:
+        return 0.0, 0, 0
+    src = torch.from_numpy(host).to(dev).repeat(reps_of)
+    dl = olens[pick % n0]
+    doff = np.concatenate([[0], np.cumsum((dl + 15) & ~15)])
+    dst = torch.empty(int(doff[-1]) + 64, dtype=torch.uint8, device=dev)
+    d = np.zeros((n, 4), dtype=np.uint64)
+    d[:, 0] = src.data_ptr() + (pick // n0) * int(foff[-1]) + foff[pick % n0]
+    d[:, 1] = flens[pick % n0]
+    d[:, 2] = dst.data_ptr() + doff[:-1]
+    d[:, 3] = dl
+    descs = torch.from_numpy(d.view(np.uint8).reshape(-1)).to(dev)
+    results = torch.zeros(n * C.sizeof(api.FrameResult), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev)
+    for _ in range(2):
+        ctx.decode_batch_device(descs.data_ptr(), results.data_ptr(), n, 0, st.cuda_stream)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(steps):
+        ctx.decode_batch_device(descs.data_ptr(), results.data_ptr(), n, 0, st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    ctx.decode_batch_device(descs.data_ptr(), results.data_ptr(), n, api.FLAG_VERIFY_CHECKSUM, st.cuda_stream)
+    torch.cuda.synchronize(dev)
+    res = results.cpu().numpy().view(RES_DT)
+    assert (res["status"] == 0).all(), f"{int((res['status'] != 0).sum())} frames failed"
+    assert (res["bytes_written"] == dl.astype(np.uint64)).all() and (res["finished"] == 1).all()
+    assert (res["chk_calc"] == res["chk_data"]).all(), "XXH64 of an output != its frame trailer"
+    k = n - 1
+    o = int(doff[k])
+    assert dst[o:o + int(dl[k])].cpu().numpy().tobytes() == origs[int(pick[k]) % n0]
+    return ms, int(dl.sum()), int(flens[pick % n0].sum())
+
+
+def other_configs(args, ctx, torch, dev, peak):
+    """config3/4/5 on one GPU (rank 0, N=1): device-timed, all outputs verified by XXH64."""
+    from cairo_zstd_b200 import workloads as W
+    out = {}
+    specs = [
+        ("config3", "literal-heavy: 1024 frames of 1 MiB (16 distinct x 64), 128 KiB blocks, 4-stream Huffman with treeless tables, raw and RLE blocks",
+         lambda: W.config3_literal_heavy(16), 64),
+        ("config4", "long window: 64 frames of 17 MiB (2 distinct x 32), windowLog 23, matches ~6 MiB back",
+         lambda: W.config4_long_window(2, total=17 << 20), 32),
+        ("config5", "mixed sizes: 8192 frames of 1 KiB..4 MiB log-uniform (512 distinct x 16), level 3",
+         lambda: W.config5_mixed_sizes(512, hi=4 << 20), 16),
+    ]
+    for key, desc, gen, reps in specs:
+        frames, origs = gen()
+        n0 = len(frames)
+        ms, ob, cb = device_time_frames(ctx, torch, dev, frames, origs, np.arange(n0 * reps), reps)
+        out[key] = {"value": ob / ms / 1e6, "unit": "GB/s", "ms": ms, "frames": n0 * reps, "out_bytes": ob, "ratio": ob / cb,
+                    "frac_of_hbm_peak": (ob + cb) / ms / 1e6 / peak, "workload": desc,
+                    "verified": "status, size and device XXH64 == trailer for every frame"}
+        torch.cuda.empty_cache()
+    return out
+
+
+def config5_sharded(args, ctx, torch, dev, dist, rank, world):
+    """BASELINE config 5 as north_star states it: ONE mixed-size batch, the same at every N, sharded over the ranks by the host
+    (czb_partition_frames: largest first by compressed + decoded bytes), no collective on the data path.  Strong scaling:
+    value = whole-batch decoded bytes / max-over-ranks device time."""
+    import cairo_zstd_b200 as czb
+    from cairo_zstd_b200 import workloads as W
+    frames, origs = W.config5_mixed_sizes(512, hi=4 << 20)   # seeded: identical on every rank
+    n0, reps = len(frames), 16
+    n = n0 * reps
+    cost = np.array([len(f) + len(o) for f, o in zip(frames, origs)], dtype=np.int64)
+    cost_all = cost[np.arange(n) % n0]
+    shard_of, load = czb.partition_frames([int(x) for x in cost_all], world)
+    pick = np.nonzero(np.asarray(shard_of) == rank)[0]
+    ms, ob, cb = device_time_frames(ctx, torch, dev, frames, origs, pick, reps)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank = [torch.zeros_like(t) for _ in range(world)] if dist is not None else [t]
+    if dist is not None:
+        dist.all_gather(per_rank, t)
+    ms_ranks = [float(x.item()) for x in per_rank]
+    total_out = int(np.array([len(o) for o in origs], dtype=np.int64).sum()) * reps
+    return {"value": total_out / max(ms_ranks) / 1e6, "unit": "GB/s", "scaling": "strong", "frames": n, "out_bytes": total_out,
+            "ms_max_over_ranks": max(ms_ranks), "ms_per_rank": ms_ranks,
+            "shard_cost_bytes": [int(x) for x in load],
+            "imbalance": max(load) / (sum(load) / world) - 1.0,
+            "partition": "czb_partition_frames (C ABI): largest first by compressed + decoded bytes",
+            "workload": "mixed sizes: 8192 frames of 1 KiB..4 MiB log-uniform (512 distinct x 16), the same batch at every N",
+            "verified": "status, size and device XXH64 == trailer for every frame of every shard"}
+
+
+def link_ceiling(torch, dev, dist, h2d_bytes, d2h_bytes, h_src, h_dst):
+    """Raw concurrent H2D + D2H of the same byte counts as one e2e step, no decode: what the host link gives this rank while
+    every other rank does the same.  Returns seconds (max over ranks)."""
+    cudart = torch.cuda.cudart()
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    chunk = 1 << 30
+    d_in = torch.empty(min(h2d_bytes, chunk), dtype=torch.uint8, device=dev)
+    d_out = torch.empty(min(d2h_bytes, chunk), dtype=torch.uint8, device=dev)
+    hs = torch.from_numpy(h_src)
+    hd = torch.from_numpy(h_dst)
+
+    def one():
+        with torch.cuda.stream(s_in):
+            for o in range(0, h2d_bytes, chunk):
+                m = min(chunk, h2d_bytes - o)
+                d_in[:m].copy_(hs[o:o + m], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for o in range(0, d2h_bytes, chunk):
+                m = min(chunk, d2h_bytes - o)
+                hd[o:o + m].copy_(d_out[:m], non_blocking=True)
+        s_in.synchronize(); s_out.synchronize()
+
+    one()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    one()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del cudart
+    return float(t.item())
+
 
 
 def run_e2e(args, ctx, frames, origs, flens, n_dev_frames, dev, dist, torch):
@@ -420,10 +579,22 @@ def run_e2e(args, ctx, frames, origs, flens, n_dev_frames, dev, dist, torch):
         dist.all_reduce(b, op=dist.ReduceOp.SUM)
     dt_max = float(t.item())
     value = float(b.item()) * args.e2e_steps / dt_max / 1e9
+    ceiling = None
+    if not args.no_link_ceiling:
+        try:
+            # torch sees the registered numpy memory as pinned only through its own allocator; non_blocking copies from
+            # cudaHostRegister'ed memory still run at full link rate (the driver recognises the registration)
+            sec = link_ceiling(torch, dev, dist, int(src_off[-1]), int(n * FRAME_SIZE), h_src, h_dst)
+            ceiling = float(b.item()) / sec / 1e9
+        except Exception as e:  # the ceiling is context, never a reason to lose the bench line
+            ceiling = None
+            sys.stderr.write(f"link ceiling skipped: {e}\n")
     for a in (h_src, h_dst, h_res):
         cudart.cudaHostUnregister(a.ctypes.data)
     world = dist.get_world_size() if dist is not None else 1
-    return {"value": value, "unit": "GB/s", "h2d_bytes_per_step": int(src_off[-1]) * world, "d2h_bytes_per_step": int(n * FRAME_SIZE) * world,
+    return {"value": value, "link_ceiling": ceiling, "frac_of_link": (value / ceiling) if ceiling else None,
+            "link_ceiling_note": "decoded GB/s if the step were only its concurrent H2D (compressed bytes) + D2H (decoded bytes) copies, "
+                                 "all ranks at once, no decode; max over ranks", "unit": "GB/s", "h2d_bytes_per_step": int(src_off[-1]) * world, "d2h_bytes_per_step": int(n * FRAME_SIZE) * world,
             "frames_per_step": int(n) * world, "steps": args.e2e_steps, "ms_per_step": 1e3 * dt_max / args.e2e_steps,
             "timing": "host wall clock around czb_decode_batch_host_packed (it returns when outputs are in host memory)",
             "pin_seconds": pin_s,

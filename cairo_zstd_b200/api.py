@@ -78,7 +78,7 @@ EXPORTS = [
     "czb_debug_last_wave_counts", "czb_debug_copy_blocks", "czb_debug_copy_literals", "czb_debug_copy_sequences",
     "czb_kernel_launches", "czb_profile_enable", "czb_profile_collect", "czs_status_name",
     "czb_split_frames_host", "czb_split_frames_device", "czb_frame_sizes_device", "czb_frame_sizes_host",
-    "czb_partition_frames", "czb_multi_create", "czb_multi_destroy", "czb_decode_batch_multi", "czb_multi_last_error",
+    "czb_debug_fd_device_work", "czb_debug_guard_faults", "czb_debug_flow_watchdog", "czb_partition_frames", "czb_multi_create", "czb_multi_destroy", "czb_decode_batch_multi", "czb_multi_last_error",
 ]
 
 _lib = None
@@ -132,6 +132,9 @@ def load_library():
     L.czb_kernel_launches.restype = u64
     L.czb_profile_enable.argtypes = [vp, C.c_int]
     L.czb_profile_collect.argtypes = [vp, P(C.c_double), P(u64)]
+    L.czb_debug_fd_device_work.argtypes = [vp, P(u64), P(u64)]
+    L.czb_debug_flow_watchdog.argtypes = [P(u32)]
+    L.czb_debug_guard_faults.argtypes = [vp, P(u64)]
     L.czb_split_frames_host.argtypes = [C.c_char_p, u64, P(FrameSpan), u64, P(u64), P(u64), P(u64)]
     L.czb_split_frames_device.argtypes = [vp, vp, u64, vp, u64, vp, vp]
     L.czb_frame_sizes_device.argtypes = [vp, vp, vp, u64, vp]
@@ -290,6 +293,12 @@ class Context:
         so = src_off.ctypes.data if hasattr(src_off, "ctypes") else C.addressof(src_off)
         do = dst_off.ctypes.data if hasattr(dst_off, "ctypes") else C.addressof(dst_off)
         self._check(self._L.czb_decode_batch_host_packed(self._h, src_base, so, dst_base, do, results_ptr, n, flags))
+
+    def guard_faults(self) -> int:
+        """CZB_GUARD=1 contexts: guard bytes behind the scratch buffers found overwritten so far (0 = clean)."""
+        v = C.c_uint64()
+        self._check(self._L.czb_debug_guard_faults(self._h, C.byref(v)))
+        return v.value
 
     # ---- per-kernel timing ----
     KERNEL_CLASSES = ["scan", "fill", "huff", "fse", "exec", "xxh64", "header_results", "frame_sizes"]

@@ -43,6 +43,18 @@ static int ensure(czb_context* ctx, DevBuf<T>& b, uint64_t n) {
     return CZS_OK;
 }
 
+// ---- guard mode (CZB_GUARD=1): compute-sanitizer is not available on every pool, so the scratch buffers can carry guard
+// zones instead.  Before a wave's kernels run, the 64 bytes behind the part of each scratch buffer that the wave may use
+// (exact totals from the scan) are filled with a pattern; after the wave a small kernel checks them.  A kernel that
+// writes past its slice of the literal / sequence / block scratch shows up in czb_debug_guard_faults.
+constexpr uint8_t kGuardByte = 0xA5;
+constexpr uint64_t kGuardBytes = 64;
+__global__ void k_check_guards(const uint8_t* a, const uint8_t* b, const uint8_t* c, unsigned long long* faults) {
+    const unsigned t = threadIdx.x;  // 3 x 64 guard bytes, one thread each
+    const uint8_t* p = t < 64 ? a : (t < 128 ? b : c);
+    if (p && p[t & 63] != kGuardByte) atomicAdd(faults, 1ull);
+}
+
 extern "C" int czb_abi_version(void) { return CZB_ABI_VERSION; }
 
 extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out) {
@@ -66,6 +78,7 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     if (setup_huff_attributes() != 0 || setup_fse_attributes() != 0 || setup_exec_attributes() != 0 || setup_exec_flow_attributes() != 0) { czb_context_destroy(ctx); return CZS_CUDA_ERROR; }
     // frames whose compressed size is at least 2^big_cls bytes get a whole CTA in sequence execution (k_exec_big)
     // and whose sequences are sparse (at least big_seq_bytes compressed bytes per sequence; 0 = any).  Knobs for tests.
+    if (const char* e = getenv("CZB_GUARD")) ctx->guard = atoi(e) != 0;
     if (const char* e = getenv("CZB_BIG_FLOW")) ctx->big_flow = atoi(e) != 0;  // 0: the round-1 in-order executor (k_exec_big), for A/B
     if (const char* e = getenv("CZB_BIG_CLS")) ctx->big_cls = atoi(e);
     if (const char* e = getenv("CZB_BIG_SEQ_BYTES")) ctx->big_seq_bytes = atoi(e);
@@ -111,7 +124,7 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p);
+    cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p); cudaFree(ctx->guard_faults.p);
     for (int s = 0; s < 2; s++) {
         cudaFree(ctx->exec_order[s].p); cudaFree(ctx->huf_cls0[s].p); cudaFree(ctx->huf_cls1[s].p); cudaFree(ctx->huf_recs[s].p);
         cudaFree(ctx->blocks[s].p); cudaFree(ctx->huf_items[s].p); cudaFree(ctx->fse_items[s].p); cudaFree(ctx->lit[s].p);
@@ -180,9 +193,10 @@ static uint64_t wave_scratch_bytes(const WaveTotals& t) {
 
 constexpr uint32_t kFlagSizesOnly = 0x80000000u;  // internal: scan + block walk + k_fse, then k_frame_sizes (czb_frame_sizes_*)
 
-// The hot path.  descs/results are device arrays.
-extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
-                                       uint32_t flags, void* stream_v) {
+// The hot path.  descs/results are device arrays.  `resume` (device array, one entry per frame, or nullptr) is the handle's
+// way of continuing frames whose first blocks were executed by earlier calls (czb_handle.cu).
+int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
+                                   uint32_t flags, void* stream_v, const FrameResume* resume) {
     if (!ctx || (n && (!descs || !results))) return CZS_BAD_ARGUMENT;
     if (n == 0) return CZS_OK;
     if (n > 0xFFFFFF00ull) { ctx->last_error = "more than 2^32 frames per call"; return CZS_BAD_ARGUMENT; }
@@ -206,7 +220,7 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
         n_waves = (n + W - 1) / W;
         if (attempt == 0) {
             CZB_CUDA(ctx, cudaMemsetAsync(ctx->totals_d.p, 0, n_waves * sizeof(WaveTotals), stream));
-            { ProfScope ps(ctx, stream, 0); launch_scan_frames(lc, descs, ctx->infos.p, n, W, ctx->totals_d.p); }
+            { ProfScope ps(ctx, stream, 0); launch_scan_frames(lc, descs, ctx->infos.p, n, W, ctx->totals_d.p, resume); }
         } else {
             launch_wave_totals(lc, ctx->infos.p, n, W, ctx->totals_d.p, n_waves);
         }
@@ -227,15 +241,15 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
     const int n_sets = (n_waves > 1 && !ctx->no_overlap) ? 2 : 1;
     for (int s = 0; s < n_sets; s++) {
         if ((rc = ensure(ctx, ctx->counters[s], 1))) return rc;
-        if ((rc = ensure(ctx, ctx->blocks[s], mx.n_blocks + 1))) return rc;
+        if ((rc = ensure(ctx, ctx->blocks[s], mx.n_blocks + 2))) return rc;
         if ((rc = ensure(ctx, ctx->huf_items[s], mx.n_huf + 1))) return rc;
         if ((rc = ensure(ctx, ctx->exec_order[s], W + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_cls0[s], mx.n_huf + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_cls1[s], mx.n_huf + 1))) return rc;
         if ((rc = ensure(ctx, ctx->huf_recs[s], mx.n_huf + 1))) return rc;
         if ((rc = ensure(ctx, ctx->fse_items[s], mx.n_fse + 1))) return rc;
-        if ((rc = ensure(ctx, ctx->lit[s], mx.lit_bytes + 64))) return rc;
-        if ((rc = ensure(ctx, ctx->seq[s], mx.n_seq + 2))) return rc;
+        if ((rc = ensure(ctx, ctx->lit[s], mx.lit_bytes + 64 + kGuardBytes))) return rc;
+        if ((rc = ensure(ctx, ctx->seq[s], mx.n_seq + 2 + kGuardBytes / sizeof(Seq)))) return rc;
     }
 
     { ProfScope ps(ctx, stream, 6); launch_header_results(lc, ctx->infos.p, results, n); }
@@ -265,8 +279,15 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
             if (count > (uint64_t)ctx->big_resident) share_bytes = std::max<uint64_t>(share_bytes, (uint64_t)t.src_bytes * 3 / (2 * count) + 1);
         }
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
+        if (ctx->guard) {
+            if ((rc = ensure(ctx, ctx->guard_faults, 1))) return rc;
+            if (!ctx->guard_zeroed) { CZB_CUDA(ctx, cudaMemsetAsync(ctx->guard_faults.p, 0, sizeof(unsigned long long), stream)); ctx->guard_zeroed = true; }
+            CZB_CUDA(ctx, cudaMemsetAsync(ctx->lit[s].p + t.lit_bytes, kGuardByte, kGuardBytes, stream));
+            CZB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->seq[s].p + t.n_seq), kGuardByte, kGuardBytes, stream));
+            CZB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(ctx->blocks[s].p + t.n_blocks), kGuardByte, kGuardBytes, stream));
+        }
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
-        { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0); }
+        { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0, resume); }
         if (!(flags & kFlagSizesOnly)) { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p, ctx->huf_recs[s].p, ctx->huf_cls0[s].p, ctx->huf_cls1[s].p); }
         { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks[s].p, ctx->fse_items[s].p, ctx->counters[s].p, (uint32_t)t.n_fse, ctx->seq[s].p); }
         if (overlap) {
@@ -274,8 +295,11 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
         if (flags & kFlagSizesOnly) { ProfScope ps(ctx, xs, 7); launch_frame_sizes(lx, ctx->infos.p, first, count, ctx->blocks[s].p, results); }
-        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join, ctx->big_flow}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join, ctx->big_flow, resume}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if ((flags & CZB_FLAG_VERIFY_CHECKSUM) && !(flags & kFlagSizesOnly)) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
+        if (ctx->guard)
+            k_check_guards<<<1, 192, 0, xs>>>(ctx->lit[s].p + t.lit_bytes, reinterpret_cast<const uint8_t*>(ctx->seq[s].p + t.n_seq),
+                                              reinterpret_cast<const uint8_t*>(ctx->blocks[s].p + t.n_blocks), ctx->guard_faults.p);
         if (overlap) CZB_CUDA(ctx, cudaEventRecord(ctx->ev_exec[s], xs));
         ctx->last_wave = t; ctx->last_wave_first = first; ctx->last_wave_count = count; ctx->last_set = s;
     }
@@ -289,8 +313,13 @@ extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* d
     return CZS_OK;
 }
 
+extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
+                                       uint32_t flags, void* stream_v) {
+    return czb_decode_batch_device_resume(ctx, descs, results, n, flags & ~kFlagSizesOnly, stream_v, nullptr);
+}
+
 extern "C" int czb_frame_sizes_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n, void* stream_v) {
-    return czb_decode_batch_device(ctx, descs, results, n, kFlagSizesOnly, stream_v);
+    return czb_decode_batch_device_resume(ctx, descs, results, n, kFlagSizesOnly, stream_v, nullptr);
 }
 
 // ---- host-pointer forms ---------------------------------------------------------------------
@@ -477,7 +506,7 @@ extern "C" int czb_frame_sizes_host(czb_context* ctx, const czb_frame_desc* desc
     cudaStream_t st = ctx->compute;
     CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_src[0].p, ctx->pin_a, stot, cudaMemcpyHostToDevice, st));
     CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_descs.p, hd, n * sizeof(czb_frame_desc), cudaMemcpyHostToDevice, st));
-    if ((rc = czb_decode_batch_device(ctx, ctx->h_descs.p, ctx->h_results.p, n, kFlagSizesOnly, st))) return rc;
+    if ((rc = czb_decode_batch_device_resume(ctx, ctx->h_descs.p, ctx->h_results.p, n, kFlagSizesOnly, st, nullptr))) return rc;
     CZB_CUDA(ctx, cudaMemcpyAsync(ctx->pin_b, ctx->h_results.p, n * sizeof(czb_frame_result), cudaMemcpyDeviceToHost, st));
     CZB_CUDA(ctx, cudaStreamSynchronize(st));
     memcpy(results, ctx->pin_b, n * sizeof(czb_frame_result));
@@ -628,6 +657,17 @@ extern "C" int czb_find_frame_end_host(const uint8_t* src, uint64_t src_len, uin
 }
 
 // ---- debug taps ---------------------------------------------------------------------------------
+extern "C" int czb_debug_guard_faults(czb_context* ctx, uint64_t* faults) {  // CZB_GUARD=1: guard bytes found overwritten so far
+    if (!ctx || !faults) return CZS_BAD_ARGUMENT;
+    *faults = 0;
+    if (!ctx->guard || !ctx->guard_faults.p) return CZS_OK;
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    CZB_CUDA(ctx, cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CZB_CUDA(ctx, cudaMemcpy(&v, ctx->guard_faults.p, sizeof v, cudaMemcpyDeviceToHost));
+    *faults = v;
+    return CZS_OK;
+}
 extern "C" int czb_debug_last_wave_counts(czb_context* ctx, uint64_t* n_blocks, uint64_t* lit_bytes, uint64_t* n_seq) {
     if (!ctx) return CZS_BAD_ARGUMENT;
     if (n_blocks) *n_blocks = ctx->last_wave.n_blocks;

@@ -2,8 +2,11 @@
 // of the batch path.  The handle keeps the reference's observable state (block_counter,
 // bytes_read_counter, frame_finished, check_sum, DecodeBuffer len/head/window) on the host and
 // lets the GPU do all decoding: whenever blocks beyond what has been decoded are asked for, the
-// source bytes seen so far are decoded as one frame on the device, and the per-block byte
-// counts written by k_exec drive the incremental strategies (UptoBlocks / UptoBytes :202-214,
+// blocks that have become available since the last run are decoded on the device -- the run
+// RESUMES after the blocks already executed (FrameResume: their output stays in the handle's
+// device buffer, offset history and counters are carried over, table-reuse chains are re-derived
+// from the source), so a frame fed in small pieces costs O(frame), not O(frame^2) -- and the
+// per-block byte counts written by k_exec drive the incremental strategies (UptoBlocks / UptoBytes :202-214,
 // decode_from_to :245-326) and the window-limited draining (decode_buffer.cairo:135-203),
 // including RingBuffer::len ignoring `head` (ring_buffer.cairo:20-22).
 #include <algorithm>
@@ -36,9 +39,16 @@ struct czb_frame_decoder {
     bool run_complete = false;      // that run reached the last block or a hard error
     std::vector<uint8_t> out_all;   // decoded bytes of the executed blocks
     uint8_t* d_src = nullptr; uint64_t d_src_cap = 0;
+    uint64_t uploaded = 0;          // acc[0 .. uploaded) is already in d_src
     uint8_t* d_dst = nullptr; uint64_t d_dst_cap = 0;
     czb_frame_desc* d_desc = nullptr;
     czb_frame_result* d_res = nullptr;
+    FrameResume* d_resume = nullptr;
+    // resume point: blocks [0, exec_blocks) were executed by earlier runs
+    uint32_t exec_blocks = 0;
+    uint32_t hist[3] = {1, 4, 8};
+    uint64_t exec_out = 0, exec_bytes_read = 0;
+    uint64_t device_runs = 0, device_blocks = 0;  // bookkeeping for the tests: blocks executed on the device, all runs
     // reference state (frame_decoder.cairo:21-30, decode_buffer.cairo:9-15)
     bool frame_finished = false;
     uint32_t block_counter = 0;
@@ -73,6 +83,7 @@ static int fd_setup(czb_frame_decoder* fd, const uint8_t* src, uint64_t src_len,
     fd->hdr = fh; fd->window = ws;
     fd->acc.assign(src, src + fh.hdr_len);
     fd->blocks.clear(); fd->decoded_acc_len = 0; fd->run_complete = false; fd->out_all.clear();
+    fd->uploaded = 0; fd->exec_blocks = 0; fd->hist[0] = 1; fd->hist[1] = 4; fd->hist[2] = 8; fd->exec_out = 0; fd->exec_bytes_read = fh.hdr_len;
     fd->frame_finished = false; fd->block_counter = 0; fd->bytes_read_counter = fh.hdr_len;
     fd->has_check_sum = false; fd->check_sum = 0; fd->buf_len = 0; fd->head = 0; fd->abs_base = 0;
     if (consumed) *consumed = fh.hdr_len;
@@ -98,17 +109,18 @@ extern "C" int czb_fd_reset(czb_frame_decoder* fd, const uint8_t* src, uint64_t 
 extern "C" void czb_fd_free(czb_frame_decoder* fd) {
     if (!fd) return;
     cudaSetDevice(fd->ctx->device);
-    cudaFree(fd->d_src); cudaFree(fd->d_dst); cudaFree(fd->d_desc); cudaFree(fd->d_res);
+    cudaFree(fd->d_src); cudaFree(fd->d_dst); cudaFree(fd->d_desc); cudaFree(fd->d_res); cudaFree(fd->d_resume);
     delete fd;
 }
 
-// Decode everything in fd->acc on the device and rebuild fd->blocks / fd->out_all.
+// Decode the blocks of fd->acc that earlier runs have not executed yet and append to fd->blocks / fd->out_all.
 static int fd_run_device(czb_frame_decoder* fd) {
     czb_context* ctx = fd->ctx;
     FD_CUDA(fd, cudaSetDevice(ctx->device));
     const uint64_t n = fd->acc.size();
-    // host walk: which blocks are present, and an output bound
-    uint64_t bound = 0, pos = fd->hdr.hdr_len;
+    cudaStream_t st = ctx->compute;
+    // host walk over the blocks not executed yet: an output bound for them
+    uint64_t bound = fd->exec_out, pos = fd->exec_bytes_read;
     for (;;) {
         ParsedBlock pb;
         parse_block_at(fd->acc.data(), n, pos, pb);
@@ -119,39 +131,52 @@ static int fd_run_device(czb_frame_decoder* fd) {
     }
     if (fd->hdr.fcs_bytes && fd->hdr.fcs > bound && fd->hdr.fcs < MAX_FRAME_OUT) bound = fd->hdr.fcs;
     uint64_t cap = bound + 64;
+    // source: only the bytes that arrived since the last run travel to the device
     if (n + 64 > fd->d_src_cap) {
-        cudaFree(fd->d_src); fd->d_src = nullptr; fd->d_src_cap = 0;
-        FD_CUDA(fd, cudaMalloc(reinterpret_cast<void**>(&fd->d_src), n + 64 + n / 2));
-        fd->d_src_cap = n + 64 + n / 2;
+        uint8_t* nsrc = nullptr;
+        const uint64_t ncap = n + 64 + n / 2;
+        FD_CUDA(fd, cudaMalloc(reinterpret_cast<void**>(&nsrc), ncap));
+        if (fd->d_src && fd->uploaded) FD_CUDA(fd, cudaMemcpyAsync(nsrc, fd->d_src, fd->uploaded, cudaMemcpyDeviceToDevice, st));
+        FD_CUDA(fd, cudaStreamSynchronize(st));
+        cudaFree(fd->d_src);
+        fd->d_src = nsrc; fd->d_src_cap = ncap;
     }
+    if (n > fd->uploaded) FD_CUDA(fd, cudaMemcpyAsync(fd->d_src + fd->uploaded, fd->acc.data() + fd->uploaded, n - fd->uploaded, cudaMemcpyHostToDevice, st));
+    fd->uploaded = n;
     if (!fd->d_desc) FD_CUDA(fd, cudaMalloc(reinterpret_cast<void**>(&fd->d_desc), sizeof(czb_frame_desc)));
     if (!fd->d_res) FD_CUDA(fd, cudaMalloc(reinterpret_cast<void**>(&fd->d_res), sizeof(czb_frame_result)));
-    cudaStream_t st = ctx->compute;
-    FD_CUDA(fd, cudaMemcpyAsync(fd->d_src, fd->acc.data(), n, cudaMemcpyHostToDevice, st));
+    if (!fd->d_resume) FD_CUDA(fd, cudaMalloc(reinterpret_cast<void**>(&fd->d_resume), sizeof(FrameResume)));
+    const FrameResume rs{fd->exec_blocks, fd->hist[0], fd->hist[1], fd->hist[2], fd->exec_out, fd->exec_bytes_read};
+    FD_CUDA(fd, cudaMemcpyAsync(fd->d_resume, &rs, sizeof rs, cudaMemcpyHostToDevice, st));
     czb_frame_result res{};
     for (;;) {
-        if (cap > fd->d_dst_cap) {
-            cudaFree(fd->d_dst); fd->d_dst = nullptr; fd->d_dst_cap = 0;
-            FD_CUDA(fd, cudaMalloc(reinterpret_cast<void**>(&fd->d_dst), cap));
-            fd->d_dst_cap = cap;
+        if (cap > fd->d_dst_cap) {  // grow, keeping the output of the executed blocks (later matches read it)
+            uint8_t* ndst = nullptr;
+            const uint64_t ncap = cap + cap / 2;
+            FD_CUDA(fd, cudaMalloc(reinterpret_cast<void**>(&ndst), ncap));
+            if (fd->d_dst && fd->exec_out) FD_CUDA(fd, cudaMemcpyAsync(ndst, fd->d_dst, fd->exec_out, cudaMemcpyDeviceToDevice, st));
+            FD_CUDA(fd, cudaStreamSynchronize(st));
+            cudaFree(fd->d_dst);
+            fd->d_dst = ndst; fd->d_dst_cap = ncap;
         }
         czb_frame_desc d{fd->d_src, n, fd->d_dst, fd->d_dst_cap};
         FD_CUDA(fd, cudaMemcpyAsync(fd->d_desc, &d, sizeof d, cudaMemcpyHostToDevice, st));
-        int rc = czb_decode_batch_device(ctx, fd->d_desc, fd->d_res, 1, 0, st);
+        int rc = czb_decode_batch_device_resume(ctx, fd->d_desc, fd->d_res, 1, 0, st, fd->d_resume);
         if (rc != CZS_OK) return rc;
         FD_CUDA(fd, cudaMemcpyAsync(&res, fd->d_res, sizeof res, cudaMemcpyDeviceToHost, st));
         FD_CUDA(fd, cudaStreamSynchronize(st));
         if (res.status != CZS_DST_TOO_SMALL || cap >= MAX_FRAME_OUT) break;
         cap = std::min<uint64_t>(cap * 4, MAX_FRAME_OUT);  // a block may legally exceed 128 KiB in the reference
     }
-    // per-block records
+    fd->device_runs++;
+    // per-block records of the blocks from the resume point on
     const uint64_t nb = ctx->last_wave.n_blocks;
     std::vector<BlockDesc> bd(nb);
     if (nb) FD_CUDA(fd, cudaMemcpy(bd.data(), ctx->blocks[ctx->last_set].p, nb * sizeof(BlockDesc), cudaMemcpyDeviceToHost));
-    fd->blocks.clear();
-    uint64_t produced = 0;
+    fd->blocks.resize(fd->exec_blocks);  // drop the record of a block that could not be read last time: it is re-examined
+    uint64_t produced = fd->exec_out;
     bool complete = false;
-    for (uint64_t k = 0; k < nb; k++) {
+    for (uint64_t k = fd->exec_blocks; k < nb; k++) {
         const BlockDesc& b = bd[k];
         BlockRec r{};
         if (b.type == BT_ERROR) {
@@ -162,15 +187,21 @@ static int fd_run_device(czb_frame_decoder* fd) {
         }
         r.last = b.last;
         r.body_bytes = b.type == BT_RLE ? 1u : b.size;
-        if (k < res.blocks_decoded) { r.status = CZS_OK; r.out_bytes = b.out_bytes; produced += b.out_bytes; }
-        else { r.status = res.status; fd->blocks.push_back(r); complete = true; break; }
-        fd->blocks.push_back(r);
+        if (k < res.blocks_decoded) {
+            r.status = CZS_OK; r.out_bytes = b.out_bytes; produced += b.out_bytes;
+            fd->blocks.push_back(r);
+            fd->exec_blocks = (uint32_t)(k + 1);
+            fd->hist[0] = b.hist_out[0]; fd->hist[1] = b.hist_out[1]; fd->hist[2] = b.hist_out[2];
+            fd->exec_bytes_read += 3ull + r.body_bytes;
+            fd->device_blocks++;
+        } else { r.status = res.status; fd->blocks.push_back(r); complete = true; break; }
         if (b.last) { complete = true; break; }
     }
     fd->run_complete = complete;
     fd->decoded_acc_len = n;
     fd->out_all.resize(produced);
-    if (produced) FD_CUDA(fd, cudaMemcpy(fd->out_all.data(), fd->d_dst, produced, cudaMemcpyDeviceToHost));
+    if (produced > fd->exec_out) FD_CUDA(fd, cudaMemcpy(fd->out_all.data() + fd->exec_out, fd->d_dst + fd->exec_out, produced - fd->exec_out, cudaMemcpyDeviceToHost));
+    fd->exec_out = produced;
     return CZS_OK;
 }
 
@@ -200,6 +231,7 @@ static int fd_step_block(czb_frame_decoder* fd, bool* was_last) {
 static void fd_append_source(czb_frame_decoder* fd, const uint8_t* src, uint64_t len) {
     // the caller's span starts at the first byte not yet consumed
     if (fd->acc.size() > fd->bytes_read_counter) fd->acc.resize(fd->bytes_read_counter);
+    if (fd->uploaded > fd->acc.size()) fd->uploaded = fd->acc.size();  // the unconsumed tail is replaced by the caller's new span
     fd->acc.insert(fd->acc.end(), src, src + len);
 }
 
@@ -328,6 +360,14 @@ extern "C" int czb_fd_decode_from_to(czb_frame_decoder* fd, const uint8_t* src, 
     if (got < 0) return (int)-got;
     *written = (uint64_t)got;
     *read_len = fd->bytes_read_counter - start;
+    return CZS_OK;
+}
+
+// tests only: how much device work the handle has caused so far (runs, blocks executed over all runs)
+extern "C" int czb_debug_fd_device_work(const czb_frame_decoder* fd, uint64_t* runs, uint64_t* blocks) {
+    if (!fd) return CZS_BAD_ARGUMENT;
+    if (runs) *runs = fd->device_runs;
+    if (blocks) *blocks = fd->device_blocks;
     return CZS_OK;
 }
 

@@ -48,6 +48,9 @@ struct czb_context {
     int share_cls = 15;         // ... or, from 2^share_cls compressed bytes on, if they hold at least 1/big_share of their wave's
     int big_resident = 1036;    //     (with more frames than resident CTAs in the wave: and at least 1.5x the mean frame)
     int big_share = 8192;       //     compressed bytes: one warp would still be on such a frame when the others have finished
+    bool guard = false;         // CZB_GUARD=1: guard zones behind the used part of the scratch buffers, checked after every wave
+    bool guard_zeroed = false;
+    DevBuf<unsigned long long> guard_faults;
     bool big_flow = true;       // CTA-per-frame executor: k_exec_flow (data-flow order) or k_exec_big (in-order commit)
     cudaStream_t big_stream = nullptr;  // k_exec_big runs beside k_exec (its CTAs are latency bound and leave most issue slots free)
     cudaEvent_t ev_big_fork = nullptr, ev_big_join = nullptr;
@@ -73,3 +76,7 @@ struct czb_context {
     czb::WaveTotals last_wave{};
     uint64_t last_wave_first = 0, last_wave_count = 0;
 };
+
+// internal (czb_handle.cu): the batch entry point with per-frame resume points
+int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n, uint32_t flags,
+                                   void* stream, const czb::FrameResume* resume);

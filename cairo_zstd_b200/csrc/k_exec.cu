@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
                                                            BigRule rule, uint32_t n_exec, WaveCounters* __restrict__ counters, const uint32_t* __restrict__ exec_order,
                                                            BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
-                                                           czb_frame_result* __restrict__ results) {
+                                                           czb_frame_result* __restrict__ results, const FrameResume* __restrict__ resume) {
     __shared__ ExecWarpSmem smem[EXEC_WARPS];
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
     ExecWarpSmem& sm = smem[warp];
@@ -199,8 +199,9 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
     uint32_t n_done = 0;
     uint64_t bytes_read = fi.hdr_len;
     bool finished = false;
+    if (resume) { const FrameResume r = resume[f]; out = r.out0; h0 = r.h0; h1 = r.h1; h2 = r.h2; n_done = r.start_block; bytes_read = r.bytes_read0; }
 
-    for (uint32_t k = 0; k < fi.n_blocks && status == CZS_OK; k++) {
+    for (uint32_t k = n_done; k < fi.n_blocks && status == CZS_OK; k++) {
         const BlockDesc d = blocks[fi.block_base + k];
         const uint64_t out_before = out;
         if (d.type == BT_ERROR) { status = d.pre_status; break; }
@@ -376,7 +377,10 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
             bytes_read += 3ull + d.size;
         }
         n_done++;
-        if (lane == 0) blocks[fi.block_base + k].out_bytes = (uint32_t)(out - out_before);
+        if (lane == 0) {  // what the FrameDecoder handle needs to continue after this block (FrameResume)
+            BlockDesc& bd = blocks[fi.block_base + k];
+            bd.out_bytes = (uint32_t)(out - out_before); bd.hist_out[0] = h0; bd.hist_out[1] = h1; bd.hist_out[2] = h2;
+        }
         if (d.last) {
             finished = true;
             if ((fi.descriptor >> 2) & 1) bytes_read += 4;  // the trailer was verified present by the scan (else a pseudo block follows)
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
                                                            BigRule rule,
                                                            const uint32_t* __restrict__ exec_order, BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
-                                                           czb_frame_result* __restrict__ results) {
+                                                           czb_frame_result* __restrict__ results, const FrameResume* __restrict__ resume) {
     extern __shared__ __align__(16) uint8_t big_raw[];
     BigSmem& sm = *reinterpret_cast<BigSmem*>(big_raw);
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -492,6 +496,9 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
     uint32_t n_done = 0, gc_base = 0;
     uint64_t bytes_read = fi.hdr_len;
     bool finished = false;
+    if (resume) { const FrameResume r = resume[f]; out = r.out0; h0 = r.h0; h1 = r.h1; h2 = r.h2; n_done = r.start_block; bytes_read = r.bytes_read0; }
+    if (threadIdx.x == 0) sm.committed_out = out;
+    __syncthreads();
 
 #ifdef CZB_BIG_CLOCK
     long long dbg_t0 = clock64();
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
 #else
     long long* dbg = nullptr;
 #endif
-    for (uint32_t k = 0; k < fi.n_blocks && status == CZS_OK; k++) {
+    for (uint32_t k = n_done; k < fi.n_blocks && status == CZS_OK; k++) {
         CLK_MARK(9);
         const BlockDesc d = blocks[fi.block_base + k];
         const uint64_t out_before = out;
@@ -709,7 +716,10 @@ __global__ void __launch_bounds__(BIG_WARPS * 32, BIG_MIN_CTAS) k_exec_big(const
             bytes_read += 3ull + d.size;
         }
         n_done++;
-        if (threadIdx.x == 0) blocks[fi.block_base + k].out_bytes = (uint32_t)(out - out_before);
+        if (threadIdx.x == 0) {
+            BlockDesc& bd = blocks[fi.block_base + k];
+            bd.out_bytes = (uint32_t)(out - out_before); bd.hist_out[0] = h0; bd.hist_out[1] = h1; bd.hist_out[2] = h2;
+        }
         if (d.last) {
             finished = true;
             if ((fi.descriptor >> 2) & 1) bytes_read += 4;
@@ -757,9 +767,9 @@ void launch_exec(const LaunchCtx& lc, const ExecSide& side, int sm_count, const 
         cudaStreamWaitEvent(side.stream, side.fork, 0);
         if (side.flow) {
             LaunchCtx ls{side.stream, lc.launches};
-            launch_exec_flow(ls, n_big_cls, descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+            launch_exec_flow(ls, n_big_cls, descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first, side.resume ? side.resume + first : nullptr);
         } else {
-            k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), side.stream>>>(descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+            k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), side.stream>>>(descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first, side.resume ? side.resume + first : nullptr);
             ++*lc.launches;
         }
         cudaEventRecord(side.join, side.stream);
@@ -767,7 +777,7 @@ void launch_exec(const LaunchCtx& lc, const ExecSide& side, int sm_count, const 
     const uint64_t want = ((uint64_t)n_exec + EXEC_WARPS - 1) / EXEC_WARPS;
     const uint64_t persistent = (uint64_t)sm_count * EXEC_CTAS_PER_SM;  // per device: the context carries its own SM count
     const unsigned grid = (unsigned)(want < persistent ? want : persistent);
-    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, rule, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first);
+    k_exec<<<grid, EXEC_WARPS * 32, 0, lc.stream>>>(descs + first, infos + first, rule, n_exec, counters, exec_order, blocks, lit_scratch, seq_scratch, results + first, side.resume ? side.resume + first : nullptr);
     ++*lc.launches;
     if (n_big_cls) cudaStreamWaitEvent(lc.stream, side.join, 0);
 }

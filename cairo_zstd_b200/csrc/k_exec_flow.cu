@@ -97,6 +97,19 @@ __device__ __forceinline__ void flow_bits_set(uint32_t* bm, uint32_t p, uint32_t
         lo = 0;
     }
 }
+// fast forms for n <= 32 (at most two words)
+__device__ __forceinline__ bool flow_bits_ready32(const uint32_t* bm, uint32_t p, uint32_t n) {
+    const uint32_t k = p >> 5;
+    const uint32_t w0 = vld(bm + (k & (FLOW_BITWORDS - 1))), w1 = vld(bm + ((k + 1) & (FLOW_BITWORDS - 1)));
+    const uint32_t x = __funnelshift_r(w0, w1, p & 31u), mask = 0xFFFFFFFFu >> (32u - n);
+    return (x & mask) == mask;
+}
+__device__ __forceinline__ void flow_bits_set32(uint32_t* bm, uint32_t p, uint32_t n) {
+    const uint32_t k = p >> 5;
+    const unsigned long long m = (unsigned long long)(0xFFFFFFFFu >> (32u - n)) << (p & 31u);
+    atomicOr(bm + (k & (FLOW_BITWORDS - 1)), (uint32_t)m);
+    if (m >> 32) atomicOr(bm + ((k + 1) & (FLOW_BITWORDS - 1)), (uint32_t)(m >> 32));
+}
 // the same for a long range, by the whole warp
 __device__ __forceinline__ void flow_bits_set_warp(uint32_t* bm, uint32_t p, uint32_t n, unsigned lane) {
     const uint32_t k0 = p >> 5, kl = (p + n - 1) >> 5;
@@ -123,6 +136,29 @@ __device__ __forceinline__ void flow_try_retire(FlowSmem& sm, uint32_t nb, uint3
         if (atomicCAS(&sm.head, h, h + 1u) == h) atomicMax(&sm.retired_out, batch_out0 + sm.chunk_out[h + 1]);
     }
 }
+
+// Measurement aid (-DCZB_FLOW_CLOCK): cycles per phase, accumulated by lane 0 of warp 0 of CTA 0 and printed per launch.
+#ifdef CZB_FLOW_CLOCK
+__device__ unsigned long long czb_flow_clk[24];
+#define FCLK(k) do { if (dbg) { const long long t_ = clock64(); atomicAdd(&czb_flow_clk[k], (unsigned long long)(t_ - *dbg)); *dbg = t_; } } while (0)
+#define FCNT(k, v) do { if (dbg) atomicAdd(&czb_flow_clk[k], (unsigned long long)(v)); } while (0)
+#else
+#define FCLK(k) do { } while (0)
+#define FCNT(k, v) do { } while (0)
+#endif
+
+// Debug aid (-DCZB_FLOW_WATCHDOG): a wait loop that spins too long records what it waits for in czb_flow_wd (read back with
+// czb_debug_flow_watchdog) and LEAVES the loop, so that the kernel ends instead of hanging.
+__device__ unsigned int czb_flow_wd[16];
+#ifdef CZB_FLOW_WATCHDOG
+#define FWD_DECL uint32_t wd_ = 0
+#define FWD(code, a, b, c2, d2, e, f2, g, h) { if (++wd_ > (1u << 20)) { if (atomicCAS(&czb_flow_wd[0], 0u, (unsigned)(code)) == 0u) { \
+    czb_flow_wd[1] = blockIdx.x; czb_flow_wd[2] = threadIdx.x >> 5; czb_flow_wd[3] = (a); czb_flow_wd[4] = (b); czb_flow_wd[5] = (c2); czb_flow_wd[6] = (d2); \
+    czb_flow_wd[7] = (e); czb_flow_wd[8] = (f2); czb_flow_wd[9] = (g); czb_flow_wd[10] = (h); } break; } }
+#else
+#define FWD_DECL do { } while (0)
+#define FWD(code, a, b, c2, d2, e, f2, g, h) { }
+#endif
 
 struct FlowWin {
     uint8_t* win;
@@ -156,7 +192,7 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                                                            BigRule rule,
                                                            const uint32_t* __restrict__ exec_order, BlockDesc* __restrict__ blocks,
                                                            const uint8_t* __restrict__ lit_scratch, const Seq* __restrict__ seq_scratch,
-                                                           czb_frame_result* __restrict__ results) {
+                                                           czb_frame_result* __restrict__ results, const FrameResume* __restrict__ resume) {
     extern __shared__ __align__(16) uint8_t flow_raw[];
     FlowSmem& sm = *reinterpret_cast<FlowSmem*>(flow_raw);
     const unsigned warp = threadIdx.x >> 5, lane = lane_id();
@@ -178,8 +214,13 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
     uint32_t n_done = 0;
     uint64_t bytes_read = fi.hdr_len;
     bool finished = false;
+    if (resume) { const FrameResume r = resume[f]; out = r.out0; h0 = r.h0; h1 = r.h1; h2 = r.h2; n_done = r.start_block; bytes_read = r.bytes_read0; }
 
-    for (uint32_t k = 0; k < fi.n_blocks && status == CZS_OK; k++) {
+#ifdef CZB_FLOW_CLOCK
+    long long dbg_t0 = clock64();
+    long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? &dbg_t0 : nullptr;
+#endif
+    for (uint32_t k = n_done; k < fi.n_blocks && status == CZS_OK; k++) {
         const BlockDesc d = blocks[fi.block_base + k];
         const uint64_t out_before = out;
         if (d.type == BT_ERROR) { status = d.pre_status; break; }
@@ -207,6 +248,7 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
             const uint32_t n_chunks = (d.n_seq + 31) / 32;
             uint32_t lit_total = 0, out_total = 0;  // literal / output bytes of the batches done so far
             bool failed = false;
+            FCLK(0);
             for (uint32_t cb = 0; cb < n_chunks && !failed; cb += FLOW_BATCH) {
                 const uint32_t nb = n_chunks - cb < FLOW_BATCH ? n_chunks - cb : FLOW_BATCH;
                 // ---- pre-pass: literal and output bytes of every chunk of the batch, then one exclusive scan ----
@@ -257,17 +299,38 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                 }
                 __syncthreads();
                 const uint32_t lit_batch = sm.chunk_lit[nb], out_batch = sm.chunk_out[nb];
+                FCLK(1);
 
                 // ---- chunks, claimed in order, completed in data-flow order ----
+                // The next chunk is claimed, and its record requested, while the current one is executed; the completion flag of a
+                // chunk is raised at the next point where this warp would otherwise have to wait (by then its flush has drained).
+                uint32_t c_next = 0, pend_done = NONE32;
+                if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
+                c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
+                Seq rec_next = 0ull;
+                { const uint32_t i0 = (cb + c_next) * 32 + lane; if (c_next < nb && i0 < d.n_seq) rec_next = __ldcs(seqs + i0); }
+                auto raise_done = [&]() {
+                    if (pend_done != NONE32) {
+                        flow_fence();  // the flushed bytes before the flag
+                        if (lane == 0) { sm.done[pend_done % FLOW_NSLOT] = pend_done + 1u; flow_try_retire(sm, nb, batch_out0); }
+                        pend_done = NONE32;
+                    }
+                };
                 for (;;) {
-                    uint32_t c = 0;
-                    if (lane == 0) c = atomicAdd(&sm.next_chunk, 1u);
-                    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                    const uint32_t c = c_next;
                     if (c >= nb) break;
                     const uint32_t i = (cb + c) * 32 + lane;
                     const bool have = i < d.n_seq;
+#ifndef CZB_FLOW_NO_PREFETCH
+                    const Seq rec = rec_next;
+                    if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
+                    c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
+                    { const uint32_t i1 = (cb + c_next) * 32 + lane; rec_next = (c_next < nb && i1 < d.n_seq) ? __ldcs(seqs + i1) : 0ull; }
+#else
+                    const Seq rec = have ? __ldcs(seqs + i) : 0ull;
+#endif
                     uint32_t ll = 0, ml = 0, off = 1;
-                    if (have) { const Seq rec = __ldcs(seqs + i); ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
+                    if (have) { ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
                     uint32_t lsum = ll, osum = ll + ml;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
@@ -289,12 +352,15 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                     }
                     const unsigned errm = __ballot_sync(0xFFFFFFFFu, err != CZS_OK);
                     const bool is_long = span > FLOW_SLICE;
+                    FCLK(2); FCNT(16, 1);
 
                     if (errm || is_long) {
                         // ---- alone: everything before this chunk has retired ----
-                        if (lane == 0) { while (vld(&sm.head) != c) { flow_try_retire(sm, nb, batch_out0); __nanosleep(64); } }
+                        raise_done();
+                        if (lane == 0) { FWD_DECL; while (vld(&sm.head) != c) { flow_try_retire(sm, nb, batch_out0); __nanosleep(64); FWD(1, c, vld(&sm.head), vld(&sm.next_chunk), vld(&sm.retired_out), vld(&sm.done[vld(&sm.head) % FLOW_NSLOT]), nb, 0, 0); } }
                         __syncwarp();
                         flow_fence();
+                        FCLK(3); FCNT(17, 1);
                         if (errm) {  // chunks reach this point in order (head == c), so the first failing chunk wins
                             const int32_t e = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1);
                             if (lane == 0 && c < sm.err_chunk) { sm.err_chunk = c; sm.err_status = e; }
@@ -344,23 +410,32 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                             flow_try_retire(sm, nb, batch_out0);
                         }
                         __syncwarp();
+#ifdef CZB_FLOW_NO_PREFETCH
+                        if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
+                        c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
+#endif
+                        FCLK(4);
                         continue;
                     }
 
                     // ---- window path ----
                     // wait for room: the span must lie within FLOW_INFLIGHT of the retired mark, the completion flags must not wrap,
                     // and a long chunk before this one must have retired (it moves win_lo)
+                    raise_done();
                     if (lane == 0) {
                         const uint32_t pl = sm.prev_long[c];
+                        FWD_DECL;
                         for (;;) {
                             const uint32_t hd = vld(&sm.head);
                             if (O + span <= vld(&sm.retired_out) + FLOW_INFLIGHT && c - hd < FLOW_NSLOT && (pl == 0xFFFFu || hd > pl)) break;
                             flow_try_retire(sm, nb, batch_out0);
                             __nanosleep(32);
+                            FWD(2, c, hd, vld(&sm.next_chunk), vld(&sm.retired_out), vld(&sm.done[hd % FLOW_NSLOT]), nb, O, span);
                         }
                     }
                     __syncwarp();
                     flow_fence();
+                    FCLK(5);
                     const uint32_t wl = vld(&sm.win_lo);
                     const uint32_t lo_abs = max(O > FLOW_REACH ? O - FLOW_REACH : 0u, wl);  // positions >= lo_abs live in the window
                     // literal runs: first 16 bytes per lane, tails by the whole warp
@@ -376,11 +451,12 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                     if (lit_rle) for (uint32_t t = 0; __any_sync(0xFFFFFFFFu, t < ll); t++) if (t < ll) W.wr(segA + t, (uint8_t)rle_byte);
                     __syncwarp();
                     flow_fence();
-                    if (ll) { if (ll <= 64u) flow_bits_set(sm.ready, segA, ll); }
+                    if (ll) { if (ll <= 32u) flow_bits_set32(sm.ready, segA, ll); else if (ll <= 64u) flow_bits_set(sm.ready, segA, ll); }
                     for (unsigned m = __ballot_sync(0xFFFFFFFFu, ll > 64u); m; m &= m - 1) {
                         const int j = __ffs(m) - 1;
                         flow_bits_set_warp(sm.ready, __shfl_sync(0xFFFFFFFFu, segA, j), __shfl_sync(0xFFFFFFFFu, ll, j), lane);
                     }
+                    FCLK(6);
                     // matches, in rounds: a match is copied once its own source bytes are ready.  Everything below lo_abs is retired
                     // (in dst, visible); a source at or above it is in the window and has ready bits.  A source may straddle lo_abs.
                     const uint32_t s_lo = segM - off;                        // frame position of the source (err == OK: off <= segM)
@@ -390,21 +466,21 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                     const uint32_t head_n = ml < 16u ? ml : 16u;
                     const bool all_win = s_lo >= lo_abs, all_dst = s_lo + head_n <= lo_abs;
                     auto RD = [&](uint32_t p) -> uint8_t { return p >= lo_abs ? W.rd(p) : __ldcg(dst + p); };
+                    // Round 1, per lane: every match whose source is ready now (sources below the window, literal runs, earlier chunks).
                     bool pending = ml > 0;
-                    for (uint32_t round = 0; __any_sync(0xFFFFFFFFu, pending); round++) {
+                    {
                         uint32_t r_now = 0;
                         if (lane == 0) r_now = vld(&sm.retired_out);
                         r_now = __shfl_sync(0xFFFFFFFFu, r_now, 0);
                         bool ready = false;
-                        if (pending) ready = s_end <= lo_abs || s_end <= r_now || flow_bits_ready(sm.ready, chk_lo, s_end - chk_lo);
-                        const unsigned rm = __ballot_sync(0xFFFFFFFFu, ready);
-                        if (!rm) {
-                            if (lane == 0) { flow_try_retire(sm, nb, batch_out0); __nanosleep(32); }
-                            __syncwarp();
-                            continue;
+                        if (pending) {
+                            if (s_end <= lo_abs || s_end <= r_now) ready = true;
+                            else if (s_end - chk_lo <= 32u) ready = flow_bits_ready32(sm.ready, chk_lo, s_end - chk_lo);
+                            else ready = flow_bits_ready(sm.ready, chk_lo, s_end - chk_lo);
                         }
                         flow_fence();  // acquire: the bytes behind the bits / the retired mark
-                        // first 16 bytes of every ready match that does not overlap itself and whose head lies on one side of lo_abs: per lane
+                        FCLK(8); FCNT(19, 1);
+                        // first 16 bytes of every ready match that does not overlap itself and whose head lies on one side of lo_abs
                         const bool simple = ready && off >= ml && (all_win || all_dst);
                         {
                             const uint32_t nm = simple ? head_n : 0u;
@@ -415,6 +491,7 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                             for (int q = 0; q < 4; q++) x.v[q] = all_win ? xw.v[q] : xg.v[q];
                             W.store16(segM, x, nm);
                         }
+                        FCLK(9);
                         // tails, self-overlapping matches and straddling heads: the whole warp on one match at a time
                         for (unsigned m = __ballot_sync(0xFFFFFFFFu, ready && (ml > 16u || !simple)); m; m &= m - 1) {
                             const int j = __ffs(m) - 1;
@@ -426,13 +503,58 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                         }
                         __syncwarp();
                         flow_fence();  // release: the bytes before their bits
-                        if (ready && ml <= 64u) flow_bits_set(sm.ready, segM, ml);
+                        FCLK(10);
+                        if (ready) { if (ml <= 32u) flow_bits_set32(sm.ready, segM, ml); else if (ml <= 64u) flow_bits_set(sm.ready, segM, ml); }
                         for (unsigned m = __ballot_sync(0xFFFFFFFFu, ready && ml > 64u); m; m &= m - 1) {
                             const int j = __ffs(m) - 1;
                             flow_bits_set_warp(sm.ready, __shfl_sync(0xFFFFFFFFu, segM, j), __shfl_sync(0xFFFFFFFFu, ml, j), lane);
                         }
                         pending = pending && !ready;
                         __syncwarp();
+                        FCLK(11);
+                    }
+                    // The rest, in sequence order, the whole warp on one match at a time (a chain of dependent matches moves at the
+                    // latency of one such step; a per-lane pass costs a warp ten times that whatever the number of lanes in it).  By the
+                    // time a match is reached every earlier sequence of this chunk is complete, so only the part of its source that
+                    // lies in other chunks has to be waited for.
+                    for (unsigned U = __ballot_sync(0xFFFFFFFFu, pending); U; U &= U - 1) {
+                        const int j = __ffs(U) - 1;
+                        const uint32_t dM = __shfl_sync(0xFFFFFFFFu, segM, j), n = __shfl_sync(0xFFFFFFFFu, ml, j), o = __shfl_sync(0xFFFFFFFFu, off, j);
+                        const uint32_t s0 = dM - o, e0 = s0 + (o < n ? o : n);
+                        const uint32_t w_lo = s0 > lo_abs ? s0 : lo_abs, w_hi = e0 < O ? e0 : O;  // the part that other chunks produce
+                        if (w_lo < w_hi) {
+                            raise_done();  // never wait on another chunk while holding back the completion flag of an earlier one
+                            const uint32_t k0 = w_lo >> 5, kl = (w_hi - 1) >> 5;
+                            FWD_DECL;
+                            for (;;) {
+                                // one lane reads the mark and everybody takes its value: the exit must be warp-uniform (lanes that see a
+                                // newer value would leave while the others wait for them in the vote below)
+                                uint32_t r_mark = 0;
+                                if (lane == 0) r_mark = vld(&sm.retired_out);
+                                r_mark = __shfl_sync(0xFFFFFFFFu, r_mark, 0);
+                                if (w_hi <= r_mark) break;
+                                bool ok = true;
+                                for (uint32_t kk = k0 + lane; kk <= kl; kk += 32) {
+                                    const uint32_t lo = kk == k0 ? (w_lo & 31u) : 0u, hi = kk == kl ? ((w_hi - 1) & 31u) : 31u;
+                                    const uint32_t mask = (0xFFFFFFFFu >> (31u - hi)) & (0xFFFFFFFFu << lo);
+                                    ok = ok && ((vld(sm.ready + (kk & (FLOW_BITWORDS - 1))) & mask) == mask);
+                                }
+                                if (__all_sync(0xFFFFFFFFu, ok)) break;
+                                if (lane == 0) { flow_try_retire(sm, nb, batch_out0); __nanosleep(20); }
+                                __syncwarp();
+                                FCNT(18, 1);
+                                FWD(3, c, vld(&sm.head), vld(&sm.next_chunk), vld(&sm.retired_out), w_lo, w_hi, O, lo_abs);
+                            }
+                            flow_fence();
+                        }
+                        FCLK(7);
+                        if (o >= n) for (uint32_t t = lane; t < n; t += 32) W.wr(dM + t, RD(s0 + t));
+                        else for (uint32_t t = lane; t < n; t += 32) W.wr(dM + t, RD(s0 + (t % o)));
+                        __syncwarp();
+                        flow_fence();
+                        flow_bits_set_warp(sm.ready, dM, n, lane);
+                        __syncwarp();
+                        FCLK(20); FCNT(21, 1);
                     }
                     // complete: copy the slice to dst (aligned 16-byte stores; window index and dst address agree modulo 16 when dst is
                     // 16-byte aligned; otherwise byte-wise)
@@ -450,17 +572,23 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                             for (uint32_t t = lane; t < span; t += 32) obase[t] = W.rd(O + t);
                         }
                     }
+                    FCLK(12);
                     flow_bits_clear_next(sm.ready, O, span, lane);
                     __syncwarp();
-                    flow_fence();
-                    if (lane == 0) {
-                        sm.done[c % FLOW_NSLOT] = c + 1u;
-                        flow_fence();
-                        flow_try_retire(sm, nb, batch_out0);
-                    }
-                    __syncwarp();
+                    pend_done = c;  // raised by raise_done(): an advance of the head missed there (store / load order) is made by the next poller
+#ifdef CZB_FLOW_EAGER_DONE
+                    raise_done();
+#endif
+#ifdef CZB_FLOW_NO_PREFETCH
+                    if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
+                    c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
+#endif
+                    FCLK(13);
                 }
+                raise_done();
+                FCLK(14);
                 __syncthreads();  // everything of the batch is complete in dst and visible to the whole CTA
+                FCLK(15);
                 if (sm.err_chunk != NONE32) { status = sm.err_status; failed = true; }
                 lit_total += lit_batch; out_total += out_batch;
                 __syncthreads();
@@ -488,13 +616,29 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
             bytes_read += 3ull + d.size;
         }
         n_done++;
-        if (threadIdx.x == 0) blocks[fi.block_base + k].out_bytes = (uint32_t)(out - out_before);
+        if (threadIdx.x == 0) {
+            BlockDesc& bd = blocks[fi.block_base + k];
+            bd.out_bytes = (uint32_t)(out - out_before); bd.hist_out[0] = h0; bd.hist_out[1] = h1; bd.hist_out[2] = h2;
+        }
         if (d.last) {
             finished = true;
             if ((fi.descriptor >> 2) & 1) bytes_read += 4;
         }
         __syncthreads();  // the block's output (incl. raw/rle/rest copies by all warps) is complete in dst
     }
+#ifdef CZB_FLOW_CLOCK
+    if (dbg) {
+        const double nc = (double)czb_flow_clk[16] > 0 ? (double)czb_flow_clk[16] : 1.0;
+        printf("flow clk (warp 0 of CTA 0, %llu chunks, %llu solo, %llu idle rounds, %llu work rounds), cycles per chunk of this warp:\n"
+               "  block setup %.0f | batch prepass+scan %.0f | claim+records+prefix+checks %.0f | solo wait %.0f | solo work %.0f | wait room %.0f |\n"
+               "  literals+bits %.0f | seq-phase waits %.0f | ready check %.0f | heads %.0f | tails %.0f | bits set %.0f | flush %.0f | done+retire %.0f | loop exit %.0f | batch barrier %.0f | seq-phase copies %.0f (%llu matches)\n",
+               czb_flow_clk[16], czb_flow_clk[17], czb_flow_clk[18], czb_flow_clk[19],
+               czb_flow_clk[0] / nc, czb_flow_clk[1] / nc, czb_flow_clk[2] / nc, czb_flow_clk[3] / nc, czb_flow_clk[4] / nc, czb_flow_clk[5] / nc,
+               czb_flow_clk[6] / nc, czb_flow_clk[7] / nc, czb_flow_clk[8] / nc, czb_flow_clk[9] / nc, (czb_flow_clk[10]) / nc, czb_flow_clk[11] / nc,
+               czb_flow_clk[12] / nc, czb_flow_clk[13] / nc, czb_flow_clk[14] / nc, czb_flow_clk[15] / nc, czb_flow_clk[20] / nc, czb_flow_clk[21]);
+        for (int q = 0; q < 24; q++) czb_flow_clk[q] = 0;
+    }
+#endif
     if (threadIdx.x == 0) {
         czb_frame_result r;
         r.status = status;
@@ -512,9 +656,17 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
 }
 
 void launch_exec_flow(const LaunchCtx& lc, unsigned n_ctas, const czb_frame_desc* descs, const FrameInfo* infos, BigRule rule, const uint32_t* exec_order,
-                      BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results) {
-    k_exec_flow<<<n_ctas, FLOW_WARPS * 32, sizeof(FlowSmem), lc.stream>>>(descs, infos, rule, exec_order, blocks, lit_scratch, seq_scratch, results);
+                      BlockDesc* blocks, const uint8_t* lit_scratch, const Seq* seq_scratch, czb_frame_result* results, const FrameResume* resume) {
+    k_exec_flow<<<n_ctas, FLOW_WARPS * 32, sizeof(FlowSmem), lc.stream>>>(descs, infos, rule, exec_order, blocks, lit_scratch, seq_scratch, results, resume);
     ++*lc.launches;
+}
+
+extern "C" int czb_debug_flow_watchdog(unsigned int* out16) {  // tests / debugging only: {code, cta, warp, 8 values}; code 0 = never fired
+    if (!out16) return CZS_BAD_ARGUMENT;
+    if (cudaMemcpyFromSymbol(out16, czb_flow_wd, sizeof(czb_flow_wd)) != cudaSuccess) return CZS_CUDA_ERROR;
+    unsigned int zero[16] = {0};
+    cudaMemcpyToSymbol(czb_flow_wd, zero, sizeof(zero));
+    return CZS_OK;
 }
 
 int setup_exec_flow_attributes() {

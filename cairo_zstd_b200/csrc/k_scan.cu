@@ -45,7 +45,8 @@ struct Walk {
 __device__ __forceinline__ uint64_t align16(uint64_t v) { return (v + 15) & ~15ull; }
 
 __global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __restrict__ descs, FrameInfo* __restrict__ infos,
-                                                      uint64_t n, uint64_t wave_frames, WaveTotals* __restrict__ totals) {
+                                                      uint64_t n, uint64_t wave_frames, WaveTotals* __restrict__ totals,
+                                                      const FrameResume* __restrict__ resume) {
     __shared__ unsigned int hist[2][32];
     if (threadIdx.x < 64) hist[threadIdx.x >> 5][threadIdx.x & 31] = 0;
     __syncthreads();
@@ -65,12 +66,13 @@ __global__ void __launch_bounds__(128) k_scan_frames(const czb_frame_desc* __res
         if (st == CZS_OK) {
             fi.hdr_len = fh.hdr_len; fi.fcs = fh.fcs; fi.window = ws; fi.descriptor = fh.descriptor;
             uint64_t pos = fh.hdr_len;
+            const uint32_t start_block = resume ? resume[i].start_block : 0u;  // earlier blocks need no entropy work (FrameResume)
             for (;;) {
                 ParsedBlock pb;
                 parse_block_at(src, len, pos, pb);
                 fi.n_blocks++;
                 if (pb.hdr_status != CZS_OK) break;
-                if (pb.type == BT_COMPRESSED && pb.pre_status == CZS_OK) {
+                if (pb.type == BT_COMPRESSED && pb.pre_status == CZS_OK && fi.n_blocks > start_block) {
                     if (pb.lit_type >= LT_COMPRESSED) { fi.n_huf++; fi.lit_bytes += align16((uint64_t)pb.regen + 16); }
                     if (pb.seqhdr_status == CZS_OK && pb.n_seq) { fi.n_fse++; fi.n_seq += seq_slots(pb.n_seq); fi.n_seq_true += pb.n_seq; }
                 }
@@ -165,7 +167,8 @@ __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __res
                                                       uint64_t first, uint64_t count, BlockDesc* __restrict__ blocks,
                                                       uint32_t* __restrict__ huf_items, uint32_t* __restrict__ fse_items,
                                                       WaveCounters* __restrict__ ctr, const WaveTotals* __restrict__ wt,
-                                                      uint32_t* __restrict__ exec_order, int exact_fse_classes) {
+                                                      uint32_t* __restrict__ exec_order, int exact_fse_classes,
+                                                      const FrameResume* __restrict__ resume) {
     // start of every size class in the work lists, largest class first
     __shared__ unsigned int frame_start[32], fse_start[32];
     if (threadIdx.x == 0) {
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __res
     uint32_t bidx = (uint32_t)blk_base;
     uint32_t last_huf = NONE32, last_tbl[3] = {NONE32, NONE32, NONE32};
     bool seen_seq = false;
+    const uint32_t start_block = resume ? resume[i].start_block : 0u;  // earlier blocks: descriptors (for the reuse chains) but no work items
     for (uint32_t k = 0; k < fi.n_blocks; k++, bidx++) {
         BlockDesc d;
         memset(&d, 0, sizeof d);
@@ -230,8 +234,10 @@ __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __res
                 if (pb.lit_type >= LT_COMPRESSED) {
                     if (pb.lit_type == LT_COMPRESSED) last_huf = bidx;
                     d.huf_src_blk = last_huf;
-                    d.lit_off = lit_base; lit_base += align16((uint64_t)pb.regen + 16);
-                    huf_items[huf_base++] = bidx;
+                    if (k >= start_block) {
+                        d.lit_off = lit_base; lit_base += align16((uint64_t)pb.regen + 16);
+                        huf_items[huf_base++] = bidx;
+                    }
                 }
                 if (pb.seqhdr_status == CZS_OK) {
                     d.n_seq = pb.n_seq; d.modes = pb.modes;
@@ -246,8 +252,10 @@ __global__ void __launch_bounds__(128) k_fill_blocks(const czb_frame_desc* __res
                         }
                         d.first_in_frame = seen_seq ? 0 : 1;
                         seen_seq = true;
-                        d.seq_off = seq_base; seq_base += seq_slots(pb.n_seq);
-                        fse_items[fse_pos++] = bidx;
+                        if (k >= start_block) {
+                            d.seq_off = seq_base; seq_base += seq_slots(pb.n_seq);
+                            fse_items[fse_pos++] = bidx;
+                        }
                     }
                 }
             }
@@ -345,9 +353,9 @@ void launch_publish_totals(const LaunchCtx& lc, const WaveTotals* totals_d, Wave
 }
 
 void launch_scan_frames(const LaunchCtx& lc, const czb_frame_desc* descs, FrameInfo* infos, uint64_t n, uint64_t wave_frames,
-                        WaveTotals* totals) {
+                        WaveTotals* totals, const FrameResume* resume) {
     if (!n) return;
-    k_scan_frames<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(descs, infos, n, wave_frames, totals);
+    k_scan_frames<<<(unsigned)((n + 127) / 128), 128, 0, lc.stream>>>(descs, infos, n, wave_frames, totals, resume);
     ++*lc.launches;
 }
 void launch_wave_totals(const LaunchCtx& lc, const FrameInfo* infos, uint64_t n, uint64_t wave_frames, WaveTotals* totals,
@@ -359,10 +367,10 @@ void launch_wave_totals(const LaunchCtx& lc, const FrameInfo* infos, uint64_t n,
 }
 void launch_fill_blocks(const LaunchCtx& lc, const czb_frame_desc* descs, FrameInfo* infos, uint64_t first, uint64_t count,
                         BlockDesc* blocks, uint32_t* huf_items, uint32_t* fse_items, WaveCounters* counters,
-                        const WaveTotals* wave_totals, uint32_t* exec_order, int exact_fse_classes) {
+                        const WaveTotals* wave_totals, uint32_t* exec_order, int exact_fse_classes, const FrameResume* resume) {
     if (!count) return;
     k_fill_blocks<<<(unsigned)((count + 127) / 128), 128, 0, lc.stream>>>(descs, infos, first, count, blocks, huf_items, fse_items, counters,
-                                                                          wave_totals, exec_order, exact_fse_classes);
+                                                                          wave_totals, exec_order, exact_fse_classes, resume);
     ++*lc.launches;
 }
 void launch_header_results(const LaunchCtx& lc, const FrameInfo* infos, czb_frame_result* results, uint64_t n) {

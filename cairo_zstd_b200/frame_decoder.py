@@ -175,6 +175,12 @@ class FrameDecoder:
         target += buf.raw[: wr.value]
         return rl.value, wr.value
 
+    def device_work(self):
+        """(device runs, blocks executed on the device over all runs): an incremental decode executes every block once."""
+        runs, blocks = C.c_uint64(), C.c_uint64()
+        self._L.czb_debug_fd_device_work(self._h, C.byref(runs), C.byref(blocks))
+        return runs.value, blocks.value
+
     def read(self, target: bytearray, cap: int = 1 << 26) -> int:
         buf = C.create_string_buffer(cap)
         n = self._L.czb_fd_read(self._h, buf, cap)

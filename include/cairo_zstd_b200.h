@@ -225,6 +225,14 @@ int czb_debug_copy_blocks(czb_context* ctx, czb_debug_block* out, uint64_t cap);
 int czb_debug_copy_literals(czb_context* ctx, uint8_t* out, uint64_t cap);
 int czb_debug_copy_sequences(czb_context* ctx, uint32_t* out /* 3 u32 per seq: ll, ml, offset */, uint64_t cap_seqs);
 
+/* Device work a handle has caused so far: runs, and blocks executed summed over all runs (an incremental decode of a
+ * frame executes every block once however small the feeds are). */
+int czb_debug_fd_device_work(const czb_frame_decoder* fd, uint64_t* runs, uint64_t* blocks);
+/* CZB_GUARD=1 (environment, read at context creation): guard zones behind the used part of the literal / sequence / block
+ * scratch, checked after every wave; returns how many guard bytes were found overwritten so far (0 = clean). */
+int czb_debug_guard_faults(czb_context* ctx, uint64_t* faults);
+int czb_debug_flow_watchdog(unsigned int* out16); /* -DCZB_FLOW_WATCHDOG builds: what a stuck wait loop of k_exec_flow recorded */
+
 /* Number of kernel launches issued by this context since creation (bench bookkeeping). */
 uint64_t czb_kernel_launches(const czb_context* ctx);
 

@@ -152,6 +152,9 @@ def test_decode_from_to_with_small_feeds_matches_oracle(corpus, name, feed):
         else:
             window = feed
     assert pos == len(f)
+    # incremental, not quadratic: however small the feeds, every block is executed on the device exactly once
+    runs, blocks = dec.device_work()
+    assert blocks == dec.blocks_decoded(), (runs, blocks, dec.blocks_decoded())
     # drain the rest the way a caller would: read() until nothing comes
     for _ in range(4):
         t = bytearray()
