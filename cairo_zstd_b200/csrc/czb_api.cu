@@ -278,6 +278,17 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
             share_bytes = (uint64_t)t.src_bytes / (uint64_t)ctx->big_share + 1;
             if (count > (uint64_t)ctx->big_resident) share_bytes = std::max<uint64_t>(share_bytes, (uint64_t)t.src_bytes * 3 / (2 * count) + 1);
         }
+        // Which CTA-per-frame executor: k_exec_flow gives one frame 16 warps and moves it ~1.8x faster than k_exec_big's four, but only
+        // two of its CTAs fit an SM against seven.  With more large frames in the wave than flow CTAs fit the machine at once the
+        // aggregate rate is what counts, and k_exec_big's is higher (mixed 1 KiB..4 MiB batch: 149 against 106 GB/s).
+        bool use_flow = ctx->big_flow;
+        if (use_flow && ctx->big_seq_bytes) {
+            const uint32_t share_c = share_bytes > 1 ? size_class(share_bytes - 1) : 0u;
+            const uint32_t lo_c = std::min<uint32_t>((uint32_t)ctx->big_cls, std::max<uint32_t>((uint32_t)ctx->share_cls, share_c));
+            uint64_t est = 0;
+            for (uint32_t c = lo_c; c < 32; c++) est += t.frame_cls[c];
+            use_flow = est <= 2ull * (uint64_t)ctx->sm_count;
+        }
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         if (ctx->guard) {
             if ((rc = ensure(ctx, ctx->guard_faults, 1))) return rc;
@@ -295,7 +306,7 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
         if (flags & kFlagSizesOnly) { ProfScope ps(ctx, xs, 7); launch_frame_sizes(lx, ctx->infos.p, first, count, ctx->blocks[s].p, results); }
-        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join, ctx->big_flow, resume}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join, use_flow, resume}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if ((flags & CZB_FLAG_VERIFY_CHECKSUM) && !(flags & kFlagSizesOnly)) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (ctx->guard)
             k_check_guards<<<1, 192, 0, xs>>>(ctx->lit[s].p + t.lit_bytes, reinterpret_cast<const uint8_t*>(ctx->seq[s].p + t.n_seq),

@@ -39,10 +39,10 @@ namespace czb {
 #define CZB_FLOW_MIN_CTAS 2
 #endif
 #ifndef CZB_FLOW_WIN_LOG
-#define CZB_FLOW_WIN_LOG 15
+#define CZB_FLOW_WIN_LOG 16  // swept: 15 / 16 -> 27.5 / 33 GB/s on 64 long-window frames (with the slice below)
 #endif
 #ifndef CZB_FLOW_SLICE
-#define CZB_FLOW_SLICE 2048
+#define CZB_FLOW_SLICE 4096  // 2048 / 4096 / 8192: a longer chunk runs alone (everybody waits), a larger slice leaves fewer chunks in flight
 #endif
 constexpr int FLOW_WARPS = CZB_FLOW_WARPS;
 constexpr uint32_t FLOW_WIN = 1u << CZB_FLOW_WIN_LOG, FLOW_WIN_MASK = FLOW_WIN - 1;
@@ -302,33 +302,17 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                 FCLK(1);
 
                 // ---- chunks, claimed in order, completed in data-flow order ----
-                // The next chunk is claimed, and its record requested, while the current one is executed; the completion flag of a
-                // chunk is raised at the next point where this warp would otherwise have to wait (by then its flush has drained).
-                uint32_t c_next = 0, pend_done = NONE32;
-                if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
-                c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
-                Seq rec_next = 0ull;
-                { const uint32_t i0 = (cb + c_next) * 32 + lane; if (c_next < nb && i0 < d.n_seq) rec_next = __ldcs(seqs + i0); }
-                auto raise_done = [&]() {
-                    if (pend_done != NONE32) {
-                        flow_fence();  // the flushed bytes before the flag
-                        if (lane == 0) { sm.done[pend_done % FLOW_NSLOT] = pend_done + 1u; flow_try_retire(sm, nb, batch_out0); }
-                        pend_done = NONE32;
-                    }
-                };
+                // (Measured and dropped: claiming the next chunk and requesting its record while the current one is executed, and
+                // raising a chunk's completion flag lazily at the warp's next wait -- 33 -> 22 GB/s on the long-window frames: a
+                // claimed chunk cannot start before its warp is free, and every start that is late delays its dependants.)
                 for (;;) {
-                    const uint32_t c = c_next;
+                    uint32_t c = 0;
+                    if (lane == 0) c = atomicAdd(&sm.next_chunk, 1u);
+                    c = __shfl_sync(0xFFFFFFFFu, c, 0);
                     if (c >= nb) break;
                     const uint32_t i = (cb + c) * 32 + lane;
                     const bool have = i < d.n_seq;
-#ifndef CZB_FLOW_NO_PREFETCH
-                    const Seq rec = rec_next;
-                    if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
-                    c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
-                    { const uint32_t i1 = (cb + c_next) * 32 + lane; rec_next = (c_next < nb && i1 < d.n_seq) ? __ldcs(seqs + i1) : 0ull; }
-#else
                     const Seq rec = have ? __ldcs(seqs + i) : 0ull;
-#endif
                     uint32_t ll = 0, ml = 0, off = 1;
                     if (have) { ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
                     uint32_t lsum = ll, osum = ll + ml;
@@ -356,7 +340,6 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
 
                     if (errm || is_long) {
                         // ---- alone: everything before this chunk has retired ----
-                        raise_done();
                         if (lane == 0) { FWD_DECL; while (vld(&sm.head) != c) { flow_try_retire(sm, nb, batch_out0); __nanosleep(64); FWD(1, c, vld(&sm.head), vld(&sm.next_chunk), vld(&sm.retired_out), vld(&sm.done[vld(&sm.head) % FLOW_NSLOT]), nb, 0, 0); } }
                         __syncwarp();
                         flow_fence();
@@ -410,10 +393,6 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                             flow_try_retire(sm, nb, batch_out0);
                         }
                         __syncwarp();
-#ifdef CZB_FLOW_NO_PREFETCH
-                        if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
-                        c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
-#endif
                         FCLK(4);
                         continue;
                     }
@@ -421,7 +400,6 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                     // ---- window path ----
                     // wait for room: the span must lie within FLOW_INFLIGHT of the retired mark, the completion flags must not wrap,
                     // and a long chunk before this one must have retired (it moves win_lo)
-                    raise_done();
                     if (lane == 0) {
                         const uint32_t pl = sm.prev_long[c];
                         FWD_DECL;
@@ -466,9 +444,13 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                     const uint32_t head_n = ml < 16u ? ml : 16u;
                     const bool all_win = s_lo >= lo_abs, all_dst = s_lo + head_n <= lo_abs;
                     auto RD = [&](uint32_t p) -> uint8_t { return p >= lo_abs ? W.rd(p) : __ldcg(dst + p); };
-                    // Round 1, per lane: every match whose source is ready now (sources below the window, literal runs, earlier chunks).
+                    // Rounds (multi-round resolution of back-references): in every round each lane whose source bytes are ready copies
+                    // its match -- the first 16 bytes per lane, tails by the whole warp -- and then publishes its bits.  Matches that
+                    // wait for other matches (of this chunk or of chunks in flight) take the next round.  With CZB_FLOW_SEQ_AFTER=k the
+                    // matches still pending after k rounds are taken in sequence order by the whole warp instead (measured slower:
+                    // an in-order pass makes every later match of the chunk wait behind the first one that is not ready).
                     bool pending = ml > 0;
-                    {
+                    for (uint32_t round = 0; __any_sync(0xFFFFFFFFu, pending); round++) {
                         uint32_t r_now = 0;
                         if (lane == 0) r_now = vld(&sm.retired_out);
                         r_now = __shfl_sync(0xFFFFFFFFu, r_now, 0);
@@ -477,6 +459,13 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                             if (s_end <= lo_abs || s_end <= r_now) ready = true;
                             else if (s_end - chk_lo <= 32u) ready = flow_bits_ready32(sm.ready, chk_lo, s_end - chk_lo);
                             else ready = flow_bits_ready(sm.ready, chk_lo, s_end - chk_lo);
+                        }
+                        const unsigned rm = __ballot_sync(0xFFFFFFFFu, ready);
+                        if (!rm) {
+                            if (lane == 0) { flow_try_retire(sm, nb, batch_out0); __nanosleep(32); }
+                            __syncwarp();
+                            FCLK(7); FCNT(18, 1);
+                            continue;
                         }
                         flow_fence();  // acquire: the bytes behind the bits / the retired mark
                         FCLK(8); FCNT(19, 1);
@@ -513,49 +502,6 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                         __syncwarp();
                         FCLK(11);
                     }
-                    // The rest, in sequence order, the whole warp on one match at a time (a chain of dependent matches moves at the
-                    // latency of one such step; a per-lane pass costs a warp ten times that whatever the number of lanes in it).  By the
-                    // time a match is reached every earlier sequence of this chunk is complete, so only the part of its source that
-                    // lies in other chunks has to be waited for.
-                    for (unsigned U = __ballot_sync(0xFFFFFFFFu, pending); U; U &= U - 1) {
-                        const int j = __ffs(U) - 1;
-                        const uint32_t dM = __shfl_sync(0xFFFFFFFFu, segM, j), n = __shfl_sync(0xFFFFFFFFu, ml, j), o = __shfl_sync(0xFFFFFFFFu, off, j);
-                        const uint32_t s0 = dM - o, e0 = s0 + (o < n ? o : n);
-                        const uint32_t w_lo = s0 > lo_abs ? s0 : lo_abs, w_hi = e0 < O ? e0 : O;  // the part that other chunks produce
-                        if (w_lo < w_hi) {
-                            raise_done();  // never wait on another chunk while holding back the completion flag of an earlier one
-                            const uint32_t k0 = w_lo >> 5, kl = (w_hi - 1) >> 5;
-                            FWD_DECL;
-                            for (;;) {
-                                // one lane reads the mark and everybody takes its value: the exit must be warp-uniform (lanes that see a
-                                // newer value would leave while the others wait for them in the vote below)
-                                uint32_t r_mark = 0;
-                                if (lane == 0) r_mark = vld(&sm.retired_out);
-                                r_mark = __shfl_sync(0xFFFFFFFFu, r_mark, 0);
-                                if (w_hi <= r_mark) break;
-                                bool ok = true;
-                                for (uint32_t kk = k0 + lane; kk <= kl; kk += 32) {
-                                    const uint32_t lo = kk == k0 ? (w_lo & 31u) : 0u, hi = kk == kl ? ((w_hi - 1) & 31u) : 31u;
-                                    const uint32_t mask = (0xFFFFFFFFu >> (31u - hi)) & (0xFFFFFFFFu << lo);
-                                    ok = ok && ((vld(sm.ready + (kk & (FLOW_BITWORDS - 1))) & mask) == mask);
-                                }
-                                if (__all_sync(0xFFFFFFFFu, ok)) break;
-                                if (lane == 0) { flow_try_retire(sm, nb, batch_out0); __nanosleep(20); }
-                                __syncwarp();
-                                FCNT(18, 1);
-                                FWD(3, c, vld(&sm.head), vld(&sm.next_chunk), vld(&sm.retired_out), w_lo, w_hi, O, lo_abs);
-                            }
-                            flow_fence();
-                        }
-                        FCLK(7);
-                        if (o >= n) for (uint32_t t = lane; t < n; t += 32) W.wr(dM + t, RD(s0 + t));
-                        else for (uint32_t t = lane; t < n; t += 32) W.wr(dM + t, RD(s0 + (t % o)));
-                        __syncwarp();
-                        flow_fence();
-                        flow_bits_set_warp(sm.ready, dM, n, lane);
-                        __syncwarp();
-                        FCLK(20); FCNT(21, 1);
-                    }
                     // complete: copy the slice to dst (aligned 16-byte stores; window index and dst address agree modulo 16 when dst is
                     // 16-byte aligned; otherwise byte-wise)
                     {
@@ -575,17 +521,14 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
                     FCLK(12);
                     flow_bits_clear_next(sm.ready, O, span, lane);
                     __syncwarp();
-                    pend_done = c;  // raised by raise_done(): an advance of the head missed there (store / load order) is made by the next poller
-#ifdef CZB_FLOW_EAGER_DONE
-                    raise_done();
-#endif
-#ifdef CZB_FLOW_NO_PREFETCH
-                    if (lane == 0) c_next = atomicAdd(&sm.next_chunk, 1u);
-                    c_next = __shfl_sync(0xFFFFFFFFu, c_next, 0);
-#endif
+                    flow_fence();  // the flushed bytes before the flag
+                    if (lane == 0) {
+                        sm.done[c % FLOW_NSLOT] = c + 1u;  // an advance of the head missed here (store / load order) is made by the next poller
+                        flow_try_retire(sm, nb, batch_out0);
+                    }
+                    __syncwarp();
                     FCLK(13);
                 }
-                raise_done();
                 FCLK(14);
                 __syncthreads();  // everything of the batch is complete in dst and visible to the whole CTA
                 FCLK(15);
@@ -631,7 +574,7 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, CZB_FLOW_MIN_CTAS) k_exec_flo
         const double nc = (double)czb_flow_clk[16] > 0 ? (double)czb_flow_clk[16] : 1.0;
         printf("flow clk (warp 0 of CTA 0, %llu chunks, %llu solo, %llu idle rounds, %llu work rounds), cycles per chunk of this warp:\n"
                "  block setup %.0f | batch prepass+scan %.0f | claim+records+prefix+checks %.0f | solo wait %.0f | solo work %.0f | wait room %.0f |\n"
-               "  literals+bits %.0f | seq-phase waits %.0f | ready check %.0f | heads %.0f | tails %.0f | bits set %.0f | flush %.0f | done+retire %.0f | loop exit %.0f | batch barrier %.0f | seq-phase copies %.0f (%llu matches)\n",
+               "  literals+bits %.0f | idle rounds %.0f | ready check %.0f | heads %.0f | tails %.0f | bits set %.0f | flush %.0f | done+retire %.0f | loop exit %.0f | batch barrier %.0f | seq-phase copies %.0f (%llu matches)\n",
                czb_flow_clk[16], czb_flow_clk[17], czb_flow_clk[18], czb_flow_clk[19],
                czb_flow_clk[0] / nc, czb_flow_clk[1] / nc, czb_flow_clk[2] / nc, czb_flow_clk[3] / nc, czb_flow_clk[4] / nc, czb_flow_clk[5] / nc,
                czb_flow_clk[6] / nc, czb_flow_clk[7] / nc, czb_flow_clk[8] / nc, czb_flow_clk[9] / nc, (czb_flow_clk[10]) / nc, czb_flow_clk[11] / nc,
