@@ -427,11 +427,18 @@ def other_configs(args, ctx, torch, dev, peak):
          lambda: W.config3_literal_heavy(16), 64),
         ("config4", "long window: 64 frames of 17 MiB (2 distinct x 32), windowLog 23, matches ~6 MiB back",
          lambda: W.config4_long_window(2, total=17 << 20), 32),
+        ("config4_512", "the same long-window frames as a batch that fills the machine: 512 frames of 17 MiB (2 distinct x 256)",
+         lambda: W.config4_long_window(2, total=17 << 20), 256),
         ("config5", "mixed sizes: 8192 frames of 1 KiB..4 MiB log-uniform (512 distinct x 16), level 3",
          lambda: W.config5_mixed_sizes(512, hi=4 << 20), 16),
     ]
+    cache = {}
     for key, desc, gen, reps in specs:
-        frames, origs = gen()
+        if key == "config4_512" and "config4" in cache:
+            frames, origs = cache["config4"]  # same generator, same seed
+        else:
+            frames, origs = gen()
+        cache[key] = (frames, origs)
         n0 = len(frames)
         ms, ob, cb = device_time_frames(ctx, torch, dev, frames, origs, np.arange(n0 * reps), reps)
         out[key] = {"value": ob / ms / 1e6, "unit": "GB/s", "ms": ms, "frames": n0 * reps, "out_bytes": ob, "ratio": ob / cb,

@@ -89,6 +89,8 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         ctx->sm_count = sms;
+        ctx->flow_max = 2ull * (uint64_t)sms;  // k_exec_flow CTAs that fit the machine at once
+        if (const char* e = getenv("CZB_FLOW_MAX")) ctx->flow_max = (uint64_t)atoll(e);
         ctx->big_resident = 7 * sms;  // k_exec_big CTAs that fit the machine at once (72 registers x 128 threads)
     }
     // Planning read-back buffer: host memory mapped into the device address space.  A kernel writes the
@@ -287,7 +289,7 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
             const uint32_t lo_c = std::min<uint32_t>((uint32_t)ctx->big_cls, std::max<uint32_t>((uint32_t)ctx->share_cls, share_c));
             uint64_t est = 0;
             for (uint32_t c = lo_c; c < 32; c++) est += t.frame_cls[c];
-            use_flow = est <= 2ull * (uint64_t)ctx->sm_count;
+            use_flow = est <= ctx->flow_max;
         }
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         if (ctx->guard) {

@@ -79,6 +79,9 @@ def main():
     if only == "6":  # not a BASELINE config: a mid-size batch of equal frames, to check the k_exec_big share rule
         f, o = W.config2_text_frames(64, 262144)
         outs.append(run("equal 256 KiB text frames", f, o, int(os.environ.get("CZB_PERF_REPS", "64")), ctx, dev))
+    if only == "4b":  # the same long-window frames as a batch large enough to fill the machine (throughput rather than per-frame latency)
+        f, o = W.config4_long_window(2, total=17 << 20)
+        outs.append(run("config4 long window 17 MiB frames, 512-frame batch", f, o, 256, ctx, dev))
     if only in ("", "4"):
         f, o = W.config4_long_window(2, total=17 << 20)
         outs.append(run("config4 long window 17 MiB frames", f, o, 32, ctx, dev))
