@@ -64,8 +64,8 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev) return CZS_CUDA_ERROR;
     czb_context* ctx = new czb_context();
     ctx->device = device;
-    ctx->budget = budget ? budget : (12ull << 30);
-    ctx->wave_frames = 131072;
+    ctx->budget = budget ? budget : (24ull << 30);
+    ctx->wave_frames = 262144;  // 131072 / 262144 / 524288 frames per wave: 295.9 / 298.3 / 298.6 GB/s on config 2 (fewer kernel tails)
     if (const char* e = getenv("CZB_WAVE_FRAMES")) ctx->wave_frames = (uint64_t)atoll(e) > 128 ? (uint64_t)atoll(e) : 128;  // tuning knobs
     ctx->wave_frames = (ctx->wave_frames + 127) / 128 * 128;  // k_scan_frames / k_fill_blocks: a warp or CTA never straddles two waves
     if (const char* e = getenv("CZB_BUDGET_GB")) ctx->budget = (uint64_t)atoll(e) << 30;

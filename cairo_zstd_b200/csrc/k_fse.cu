@@ -25,6 +25,9 @@ namespace czb {
 #define CZB_FSE_WARPS 4  // table-building warps per CTA (6 / 8 measured: see DESIGN.md)
 #endif
 constexpr int FSE_WARPS = CZB_FSE_WARPS;
+#ifndef CZB_FSE_QUAD
+#define CZB_FSE_QUAD 1  // four records leave as two 16-byte stores (half the store sectors); 0: one 8-byte store per sequence
+#endif
 #ifndef CZB_FSE_SLOTS
 #define CZB_FSE_SLOTS 27
 #endif
@@ -319,11 +322,16 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             using Q3 = std::integral_constant<int, 3>; using QN = std::integral_constant<int, -1>;
             uint32_t i = 0;
             for (; i + 4 < n_seq; i += 4) {
+#if CZB_FSE_QUAD
                 step(i, std::true_type{}, R0{}, Q0{}); step(i + 1, std::true_type{}, R0{}, Q1{});
                 step(i + 2, std::true_type{}, R0{}, Q2{}); step(i + 3, std::true_type{}, R3{}, Q3{});
                 uint4* o4 = reinterpret_cast<uint4*>(out + i);
                 __stcs(o4, make_uint4((uint32_t)quad[0], (uint32_t)(quad[0] >> 32), (uint32_t)quad[1], (uint32_t)(quad[1] >> 32)));
                 __stcs(o4 + 1, make_uint4((uint32_t)quad[2], (uint32_t)(quad[2] >> 32), (uint32_t)quad[3], (uint32_t)(quad[3] >> 32)));
+#else
+                step(i, std::true_type{}, R0{}, QN{}); step(i + 1, std::true_type{}, R0{}, QN{});
+                step(i + 2, std::true_type{}, R0{}, QN{}); step(i + 3, std::true_type{}, R3{}, QN{});
+#endif
             }
             for (; i + 1 < n_seq; i++) step(i, std::true_type{}, R1{}, QN{});
             step(i, std::false_type{}, R0{}, QN{});
