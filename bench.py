@@ -299,16 +299,30 @@ def run_b200(args, rank, world, local_rank):
                 "kernel_share_of_step": {k: v[0] / kernel_ms_total for k, v in prof.items()} if kernel_ms_total else {},
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
     # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per frame x frames per launch)
-    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    traffic_path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(traffic_path):
         try:
-            tk = json.load(open(traffic_path))["kernels"].get("k_" + dom_name)
+            tj = json.load(open(traffic_path))
+            tk = tj["kernels"].get("k_" + dom_name)
+            frames_per_launch = n * args.steps / max(dom_launches, 1)
             if tk:
-                roofline["traffic"] = tk["bytes_per_frame"] * n * args.steps / max(dom_launches, 1)
-                roofline["traffic_source"] = "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per frame) x frames per launch"
+                roofline["traffic"] = tk["bytes_per_frame"] * frames_per_launch
+                roofline["traffic_source"] = ("profiles/r02_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per frame from this round's "
+                                              "ncu --set full capture of the same kernels (scripts/r02_ncu.sh), x frames per launch")
                 roofline["algorithmic_bytes_per_launch"] = alg_bytes_per_launch
-        except Exception:
-            pass
+                # issue-slot fraction next to the HBM fraction: warp instructions the kernel executes (same capture) against what
+                # the SMs can issue in the kernel's live average launch time (4 schedulers per SM, one warp instruction per cycle)
+                import torch as _t
+                sms = _t.cuda.get_device_properties(dev).multi_processor_count
+                clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                roofline["issue_slots"] = {"warp_inst_per_launch": tk["warp_inst_per_frame"] * frames_per_launch,
+                                           "frac": tk["warp_inst_per_frame"] * frames_per_launch / (dom_avg_ms * 1e-3 * sms * 4 * clk),
+                                           "note": "fraction of the SMs' issue slots the dominant kernel uses; the kernel is latency / issue bound, not HBM bound"}
+            wp = sum(k["warp_inst_per_frame"] for kn, k in tj["kernels"].items())
+            roofline["whole_path"]["issue_slot_frac"] = wp * n / (ms_per_step * 1e-3 * sms * 4 * clk)
+            roofline["whole_path"]["dram_traffic_over_algorithmic"] = tj.get("whole_path_traffic_over_algorithmic")
+        except Exception as e:
+            sys.stderr.write(f"traffic/issue-slot annotation skipped: {e}\n")
 
     # ---- e2e: host buffers through czb_decode_batch_host_packed ----
     e2e = None

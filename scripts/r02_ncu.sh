@@ -1,0 +1,12 @@
+#!/bin/bash
+# round 2 ncu evidence (GPU box).  Each profiled command first runs plainly and must exit 0.
+set -x
+B="python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-other-configs"
+$B > gpurun_out/r02_ncu_plain.json 2> gpurun_out/r02_ncu_plain.err || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02_launches.csv $B > gpurun_out/r02_ncu_launches.log 2>&1
+S="python bench.py --frames 65536 --steps 1 --warmup 1 --distinct 512 --no-e2e --no-cpu-baseline --no-other-configs"
+$S > /dev/null 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k 'regex:k_fse|k_huff|k_exec|k_xxh64' -s 6 -c 6 -f -o gpurun_out/r02_full $S > gpurun_out/r02_ncu_full.log 2>&1
+python scripts/perf_configs.py 4 > /dev/null 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k 'regex:k_exec_flow' -s 2 -c 1 -f -o gpurun_out/r02_flow python scripts/perf_configs.py 4 > gpurun_out/r02_ncu_flow.log 2>&1
+ls -la gpurun_out/*.ncu-rep
