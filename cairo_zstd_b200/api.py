@@ -78,7 +78,7 @@ EXPORTS = [
     "czb_debug_last_wave_counts", "czb_debug_copy_blocks", "czb_debug_copy_literals", "czb_debug_copy_sequences",
     "czb_kernel_launches", "czb_profile_enable", "czb_profile_collect", "czs_status_name",
     "czb_split_frames_host", "czb_split_frames_device", "czb_frame_sizes_device", "czb_frame_sizes_host",
-    "czb_debug_fd_device_work", "czb_debug_guard_faults", "czb_debug_flow_watchdog", "czb_partition_frames", "czb_multi_create", "czb_multi_destroy", "czb_decode_batch_multi", "czb_multi_last_error",
+    "czb_plan_batch_device", "czb_plan_destroy", "czb_decode_batch_device_planned", "czb_debug_fd_device_work", "czb_debug_guard_faults", "czb_debug_flow_watchdog", "czb_partition_frames", "czb_multi_create", "czb_multi_destroy", "czb_decode_batch_multi", "czb_multi_last_error",
 ]
 
 _lib = None
@@ -132,6 +132,9 @@ def load_library():
     L.czb_kernel_launches.restype = u64
     L.czb_profile_enable.argtypes = [vp, C.c_int]
     L.czb_profile_collect.argtypes = [vp, P(C.c_double), P(u64)]
+    L.czb_plan_batch_device.argtypes = [vp, vp, u64, vp, P(vp)]
+    L.czb_plan_destroy.argtypes = [vp]
+    L.czb_decode_batch_device_planned.argtypes = [vp, vp, vp, vp, u64, u32, vp]
     L.czb_debug_fd_device_work.argtypes = [vp, P(u64), P(u64)]
     L.czb_debug_flow_watchdog.argtypes = [P(u32)]
     L.czb_debug_guard_faults.argtypes = [vp, P(u64)]
@@ -268,6 +271,19 @@ class Context:
     def decode_batch_device(self, descs_ptr: int, results_ptr: int, n: int, flags: int = 0, stream: int = 0):
         """descs_ptr/results_ptr: device addresses of czb_frame_desc[n] / czb_frame_result[n]."""
         self._check(self._L.czb_decode_batch_device(self._h, descs_ptr, results_ptr, n, flags, stream))
+
+    def plan_batch_device(self, descs_ptr: int, n: int, stream: int = 0):
+        """czb_plan_batch_device: returns an opaque plan handle (free with plan_destroy)."""
+        h = C.c_void_p()
+        self._check(self._L.czb_plan_batch_device(self._h, descs_ptr, n, stream, C.byref(h)))
+        return h
+
+    def plan_destroy(self, plan):
+        self._L.czb_plan_destroy(plan)
+
+    def decode_batch_device_planned(self, plan, descs_ptr: int, results_ptr: int, n: int, flags: int = 0, stream: int = 0):
+        """No host synchronisation: every kernel is only enqueued (can be captured into a CUDA graph)."""
+        self._check(self._L.czb_decode_batch_device_planned(self._h, plan, descs_ptr, results_ptr, n, flags, stream))
 
     # ---- host-pointer forms ----
     def decode_batch(self, frames, dst_caps, flags: int = 0):

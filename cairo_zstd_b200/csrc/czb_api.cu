@@ -197,9 +197,25 @@ constexpr uint32_t kFlagSizesOnly = 0x80000000u;  // internal: scan + block walk
 
 // The hot path.  descs/results are device arrays.  `resume` (device array, one entry per frame, or nullptr) is the handle's
 // way of continuing frames whose first blocks were executed by earlier calls (czb_handle.cu).
+struct czb_batch_plan {   // what the planning read-back of a batch call produces (czb_plan_batch_device)
+    uint64_t n = 0, W = 0, n_waves = 0;
+    std::vector<WaveTotals> totals;
+};
+
+static int decode_batch_impl(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n, uint32_t flags,
+                             void* stream_v, const FrameResume* resume, const czb_batch_plan* plan, czb_batch_plan* plan_out);
+
 int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
                                    uint32_t flags, void* stream_v, const FrameResume* resume) {
-    if (!ctx || (n && (!descs || !results))) return CZS_BAD_ARGUMENT;
+    return decode_batch_impl(ctx, descs, results, n, flags, stream_v, resume, nullptr, nullptr);
+}
+
+// plan != nullptr: the wave split and the per-wave totals come from an earlier czb_plan_batch_device of the same frames, so
+// nothing is read back and the host never waits: every kernel is only enqueued (graph capture, pipelining).
+// plan_out != nullptr: only plan (scan + read-back), decode nothing.
+static int decode_batch_impl(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n, uint32_t flags,
+                             void* stream_v, const FrameResume* resume, const czb_batch_plan* plan, czb_batch_plan* plan_out) {
+    if (!ctx || (n && (!descs || (!results && !plan_out)))) return CZS_BAD_ARGUMENT;
     if (n == 0) return CZS_OK;
     if (n > 0xFFFFFF00ull) { ctx->last_error = "more than 2^32 frames per call"; return CZS_BAD_ARGUMENT; }
     CZB_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -208,7 +224,11 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
     int rc;
     // The per-context scratch (infos, totals, counters, blocks, literal and sequence scratch, work lists) is reused by
     // every call: a call on another stream must not start overwriting it while the previous call's kernels still read it.
-    if (ctx->scratch_in_use) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_scratch_free, 0));
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cap_st);
+    const bool capturing = cap_st != cudaStreamCaptureStatusNone;  // a captured call is ordered by the graph it becomes part of
+    if (ctx->scratch_in_use && !capturing) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_scratch_free, 0));
+    if (plan && plan->n != n) { ctx->last_error = "plan was made for a different batch"; return CZS_BAD_ARGUMENT; }
     if ((rc = ensure(ctx, ctx->infos, n))) return rc;
     if ((rc = ensure(ctx, ctx->totals_d, kMaxWaves))) return rc;
 
@@ -217,7 +237,13 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
     while ((n + W - 1) / W > kMaxWaves) W *= 2;
     uint64_t n_waves = 0;
     bool exact_classes = true;  // per-section size classes come from the scan; a planning retry only has per-frame data
-    for (int attempt = 0;; attempt++) {
+    const WaveTotals* totals_host = ctx->totals_h;
+    if (plan) {  // scan with the planned wave size (device-side totals and size classes for k_fill_blocks), no read-back
+        W = plan->W; n_waves = plan->n_waves; totals_host = plan->totals.data();
+        CZB_CUDA(ctx, cudaMemsetAsync(ctx->totals_d.p, 0, n_waves * sizeof(WaveTotals), stream));
+        { ProfScope ps(ctx, stream, 0); launch_scan_frames(lc, descs, ctx->infos.p, n, W, ctx->totals_d.p, resume); }
+    }
+    for (int attempt = 0; !plan; attempt++) {
         exact_classes = attempt == 0;
         n_waves = (n + W - 1) / W;
         if (attempt == 0) {
@@ -233,9 +259,13 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
         if ((ctx->no_overlap ? 1 : 2) * worst <= ctx->budget || W <= 128 || (n + W / 2 - 1) / (W / 2) > kMaxWaves) break;
         W = std::max<uint64_t>(128, (W / 2 + 127) / 128 * 128);
     }
+    if (plan_out) {  // keep a final scan with the final wave size consistent: a retry recomputed totals from per-frame data
+        plan_out->n = n; plan_out->W = W; plan_out->n_waves = n_waves;
+        plan_out->totals.assign(ctx->totals_h, ctx->totals_h + n_waves);
+    }
     WaveTotals mx{};
     for (uint64_t w = 0; w < n_waves; w++) {
-        const WaveTotals& t = ctx->totals_h[w];
+        const WaveTotals& t = totals_host[w];
         mx.n_blocks = std::max(mx.n_blocks, t.n_blocks); mx.lit_bytes = std::max(mx.lit_bytes, t.lit_bytes);
         mx.n_seq = std::max(mx.n_seq, t.n_seq); mx.n_huf = std::max(mx.n_huf, t.n_huf); mx.n_fse = std::max(mx.n_fse, t.n_fse);
         if (t.n_blocks > 0xFFFFFF00ull) { ctx->last_error = "too many blocks in one wave"; return CZS_UNSUPPORTED; }
@@ -254,6 +284,7 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
         if ((rc = ensure(ctx, ctx->seq[s], mx.n_seq + 2 + kGuardBytes / sizeof(Seq)))) return rc;
     }
 
+    if (plan_out) return CZS_OK;  // scratch is sized, nothing else to do
     { ProfScope ps(ctx, stream, 6); launch_header_results(lc, ctx->infos.p, results, n); }
     // Two-stage pipeline over waves: the entropy stage (fill, Huffman, FSE: shared-memory bound, few
     // warps per SM) runs on `stream`; sequence execution (many warps, almost no shared memory) runs
@@ -268,7 +299,7 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
     for (uint64_t w = 0; w < n_waves; w++) {
         const int s = overlap ? (int)(w & 1) : 0;
         const uint64_t first = w * W, count = std::min<uint64_t>(W, n - first);
-        const WaveTotals& t = ctx->totals_h[w];
+        const WaveTotals& t = totals_host[w];
         uint32_t n_exec = 0, n_big = 0;
         for (int c = 0; c < 32; c++) { n_exec += t.frame_cls[c]; if (c >= ctx->share_cls) n_big += t.frame_cls[c]; }
         // Share rule of k_exec_big (see frame_is_big): frames that hold at least 1/big_share of the wave's compressed bytes.
@@ -320,8 +351,10 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
         CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 1) & 1], 0));
         if (n_waves > 1) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[(n_waves - 2) & 1], 0));
     }
-    CZB_CUDA(ctx, cudaEventRecord(ctx->ev_scratch_free, stream));  // after the join: every kernel of this call is ordered before it
-    ctx->scratch_in_use = true;
+    if (!capturing) {
+        CZB_CUDA(ctx, cudaEventRecord(ctx->ev_scratch_free, stream));  // after the join: every kernel of this call is ordered before it
+        ctx->scratch_in_use = true;
+    }
     CZB_CUDA(ctx, cudaGetLastError());
     return CZS_OK;
 }
@@ -329,6 +362,23 @@ int czb_decode_batch_device_resume(czb_context* ctx, const czb_frame_desc* descs
 extern "C" int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n,
                                        uint32_t flags, void* stream_v) {
     return czb_decode_batch_device_resume(ctx, descs, results, n, flags & ~kFlagSizesOnly, stream_v, nullptr);
+}
+
+extern "C" int czb_plan_batch_device(czb_context* ctx, const czb_frame_desc* descs, uint64_t n, void* stream_v, czb_batch_plan** out) {
+    if (!ctx || !out || (n && !descs)) return CZS_BAD_ARGUMENT;
+    *out = nullptr;
+    czb_batch_plan* p = new czb_batch_plan();
+    const int rc = n ? decode_batch_impl(ctx, descs, nullptr, n, 0, stream_v, nullptr, nullptr, p) : CZS_OK;
+    if (rc != CZS_OK) { delete p; return rc; }
+    *out = p;
+    return CZS_OK;
+}
+extern "C" void czb_plan_destroy(czb_batch_plan* plan) { delete plan; }
+extern "C" int czb_decode_batch_device_planned(czb_context* ctx, const czb_batch_plan* plan, const czb_frame_desc* descs,
+                                               czb_frame_result* results, uint64_t n, uint32_t flags, void* stream_v) {
+    if (!plan) return CZS_BAD_ARGUMENT;
+    if (n == 0) return CZS_OK;
+    return decode_batch_impl(ctx, descs, results, n, flags & ~kFlagSizesOnly, stream_v, nullptr, plan, nullptr);
 }
 
 extern "C" int czb_frame_sizes_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results, uint64_t n, void* stream_v) {

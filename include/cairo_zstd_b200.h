@@ -106,6 +106,17 @@ int czb_abi_version(void);
 int czb_decode_batch_device(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results,
                             uint64_t n_frames, uint32_t flags, void* stream);
 
+/* The same without the planning read-back.  czb_plan_batch_device scans the frames once, synchronises `stream`, sizes the
+ * context's scratch and keeps the wave split; czb_decode_batch_device_planned then decodes the SAME frames (same count, same
+ * compressed bytes at the same or other addresses) without any host synchronisation: every kernel is only enqueued, so the
+ * call can be pipelined behind other work or captured into a CUDA graph (inside a capture the call takes no part in the
+ * cross-stream ordering of ordinary calls: replay the graph only while no other call uses the context). */
+typedef struct czb_batch_plan czb_batch_plan;
+int czb_plan_batch_device(czb_context* ctx, const czb_frame_desc* descs, uint64_t n_frames, void* stream, czb_batch_plan** out);
+void czb_plan_destroy(czb_batch_plan* plan);
+int czb_decode_batch_device_planned(czb_context* ctx, const czb_batch_plan* plan, const czb_frame_desc* descs,
+                                    czb_frame_result* results, uint64_t n_frames, uint32_t flags, void* stream);
+
 /* Host form: descs/results and every src/dst are HOST pointers.  Copies inputs to the
  * device, decodes, copies outputs back, and returns when results are valid. */
 int czb_decode_batch_host(czb_context* ctx, const czb_frame_desc* descs, czb_frame_result* results,

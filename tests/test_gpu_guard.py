@@ -87,3 +87,52 @@ def test_no_store_leaves_its_span_and_scratch_guards_stay_intact(corpus, monkeyp
     assert (out[mask] == PAT).all(), f"{int((out[mask] != PAT).sum())} bytes outside the frames' spans were overwritten"
     assert ctx.guard_faults() == 0
     ctx.close()
+
+
+def test_planned_call_needs_no_host_sync_and_can_be_graph_captured(corpus):
+    """czb_plan_batch_device + czb_decode_batch_device_planned: same results as the ordinary call, no planning read-back; the
+    planned call is captured into a CUDA graph and replayed."""
+    import torch
+    ctx = czb.Context(0)
+    frames, caps = _frames(corpus)
+    frames, caps = frames[:140], caps[:140]   # valid frames only (corpus + synthetic)
+    n = len(frames)
+    dev = torch.device("cuda", 0)
+    flens = np.array([len(f) for f in frames], dtype=np.int64)
+    soff = np.concatenate([[0], np.cumsum((flens + 15) & ~15)])
+    src_h = np.zeros(int(soff[-1]) + 16, dtype=np.uint8)
+    for i, f in enumerate(frames):
+        src_h[soff[i]:soff[i] + len(f)] = np.frombuffer(f, dtype=np.uint8)
+    src = torch.from_numpy(src_h).to(dev)
+    caps_a = np.array(caps, dtype=np.int64)
+    doff = np.concatenate([[0], np.cumsum((caps_a + 15) & ~15)])
+    dst = torch.zeros(int(doff[-1]) + 64, dtype=torch.uint8, device=dev)
+    d = np.zeros((n, 4), dtype=np.uint64)
+    d[:, 0] = src.data_ptr() + soff[:-1]; d[:, 1] = flens; d[:, 2] = dst.data_ptr() + doff[:-1]; d[:, 3] = caps_a
+    descs = torch.from_numpy(d.view(np.uint8).reshape(-1)).to(dev)
+    res_a = torch.zeros(n * C.sizeof(api.FrameResult), dtype=torch.uint8, device=dev)
+    res_b = torch.zeros_like(res_a)
+    s = torch.cuda.Stream(dev)
+    ctx.decode_batch_device(descs.data_ptr(), res_a.data_ptr(), n, api.FLAG_VERIFY_CHECKSUM, s.cuda_stream)
+    s.synchronize()
+    want = dst.clone()
+    plan = ctx.plan_batch_device(descs.data_ptr(), n, s.cuda_stream)
+    dst.zero_()
+    ctx.decode_batch_device_planned(plan, descs.data_ptr(), res_b.data_ptr(), n, api.FLAG_VERIFY_CHECKSUM, s.cuda_stream)
+    s.synchronize()
+    assert torch.equal(dst, want) and torch.equal(res_a, res_b)
+    res = (api.FrameResult * n).from_buffer_copy(res_b.cpu().numpy().tobytes())
+    assert all(r.status == 0 and r.checksum_calculated == r.checksum_from_data for r in res)
+    # graph capture + two replays
+    g = torch.cuda.CUDAGraph()
+    dst.zero_(); res_b.zero_()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=s, capture_error_mode="relaxed"):
+        ctx.decode_batch_device_planned(plan, descs.data_ptr(), res_b.data_ptr(), n, api.FLAG_VERIFY_CHECKSUM, s.cuda_stream)
+    for _ in range(2):
+        dst.zero_(); res_b.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(dst, want) and torch.equal(res_a, res_b)
+    ctx.plan_destroy(plan)
+    ctx.close()
