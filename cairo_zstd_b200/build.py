@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcairo_zstd_b200.so")
 SOURCES = ["czb_api.cu", "czb_handle.cu", "k_scan.cu", "k_huff.cu", "k_fse.cu", "k_exec.cu", "k_exec_flow.cu", "k_xxh.cu"]
-HEADERS = ["czb_internal.cuh", "czb_parse.cuh", "czb_fse_build.cuh", "czb_host.h", "czb_exec.cuh",
+HEADERS = ["czb_internal.cuh", "czb_parse.cuh", "czb_fse_build.cuh", "czb_host.h", "czb_exec.cuh", "k_exec_flow_impl.cuh",
            "../../include/cairo_zstd_b200.h", "../../include/czstd_status.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math"]

@@ -79,6 +79,7 @@ extern "C" int czb_context_create(int device, uint64_t budget, czb_context** out
     // frames whose compressed size is at least 2^big_cls bytes get a whole CTA in sequence execution (k_exec_big)
     // and whose sequences are sparse (at least big_seq_bytes compressed bytes per sequence; 0 = any).  Knobs for tests.
     if (const char* e = getenv("CZB_GUARD")) ctx->guard = atoi(e) != 0;
+    if (const char* e = getenv("CZB_FLOW_WIDE")) ctx->flow_wide_forced = atoi(e) != 0;
     if (const char* e = getenv("CZB_BIG_FLOW")) ctx->big_flow = atoi(e) != 0;  // 0: the round-1 in-order executor (k_exec_big), for A/B
     if (const char* e = getenv("CZB_BIG_CLS")) ctx->big_cls = atoi(e);
     if (const char* e = getenv("CZB_BIG_SEQ_BYTES")) ctx->big_seq_bytes = atoi(e);
@@ -314,13 +315,15 @@ static int decode_batch_impl(czb_context* ctx, const czb_frame_desc* descs, czb_
         // Which CTA-per-frame executor: k_exec_flow gives one frame 16 warps and moves it ~1.8x faster than k_exec_big's four, but only
         // two of its CTAs fit an SM against seven.  With more large frames in the wave than flow CTAs fit the machine at once the
         // aggregate rate is what counts, and k_exec_big's is higher (mixed 1 KiB..4 MiB batch: 149 against 106 GB/s).
-        bool use_flow = ctx->big_flow;
+        bool use_flow = ctx->big_flow, flow_wide = false;
+        if (use_flow && !ctx->big_seq_bytes) flow_wide = ctx->flow_wide_forced;  // test knob: every frame through one shape
         if (use_flow && ctx->big_seq_bytes) {
             const uint32_t share_c = share_bytes > 1 ? size_class(share_bytes - 1) : 0u;
             const uint32_t lo_c = std::min<uint32_t>((uint32_t)ctx->big_cls, std::max<uint32_t>((uint32_t)ctx->share_cls, share_c));
             uint64_t est = 0;
             for (uint32_t c = lo_c; c < 32; c++) est += t.frame_cls[c];
             use_flow = est <= ctx->flow_max;
+            flow_wide = est <= (uint64_t)ctx->sm_count;  // at most one large frame per SM: the 32-warp shape with the 128 KiB window
         }
         if (overlap && w >= 2) CZB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->ev_exec[s], 0));  // scratch set s is free again
         if (ctx->guard) {
@@ -339,7 +342,7 @@ static int decode_batch_impl(czb_context* ctx, const czb_frame_desc* descs, czb_
             CZB_CUDA(ctx, cudaStreamWaitEvent(xs, ctx->ev_entropy[s], 0));
         }
         if (flags & kFlagSizesOnly) { ProfScope ps(ctx, xs, 7); launch_frame_sizes(lx, ctx->infos.p, first, count, ctx->blocks[s].p, results); }
-        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join, use_flow, resume}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
+        else { ProfScope ps(ctx, xs, 4); launch_exec(lx, ExecSide{ctx->big_stream, ctx->ev_big_fork, ctx->ev_big_join, use_flow, flow_wide, resume}, ctx->sm_count, descs, ctx->infos.p, first, count, n_big, n_exec, BigRule{(uint32_t)ctx->big_cls, (uint32_t)ctx->big_seq_bytes, (uint32_t)ctx->share_cls, share_bytes}, ctx->counters[s].p, ctx->exec_order[s].p, ctx->blocks[s].p, ctx->lit[s].p, ctx->seq[s].p, results); }
         if ((flags & CZB_FLAG_VERIFY_CHECKSUM) && !(flags & kFlagSizesOnly)) { ProfScope ps(ctx, xs, 5); launch_xxh64(lx, descs, results, first, count); }
         if (ctx->guard)
             k_check_guards<<<1, 192, 0, xs>>>(ctx->lit[s].p + t.lit_bytes, reinterpret_cast<const uint8_t*>(ctx->seq[s].p + t.n_seq),

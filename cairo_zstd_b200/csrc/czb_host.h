@@ -52,6 +52,7 @@ struct czb_context {
     bool guard_zeroed = false;
     DevBuf<unsigned long long> guard_faults;
     uint64_t flow_max = 296;    // k_exec_flow takes a wave's large frames only if there are at most this many (else k_exec_big)
+    bool flow_wide_forced = false;  // with CZB_BIG_SEQ_BYTES=0 (tests): force the 32-warp shape of k_exec_flow
     bool big_flow = true;       // CTA-per-frame executor: k_exec_flow (data-flow order) or k_exec_big (in-order commit)
     cudaStream_t big_stream = nullptr;  // k_exec_big runs beside k_exec (its CTAs are latency bound and leave most issue slots free)
     cudaEvent_t ev_big_fork = nullptr, ev_big_join = nullptr;

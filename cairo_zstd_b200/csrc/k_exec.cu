@@ -28,6 +28,9 @@
 
 namespace czb {
 
+#ifndef CZB_EXEC_PF
+#define CZB_EXEC_PF 0
+#endif
 #if EXEC_TILE_PATH
 // ---- k_exec_big's chunk executor: the frame's recent output lives in a shared-memory window ----
 // k_exec_big commits the chunks of a frame in order, so whatever a chunk does between "everything before me is
@@ -228,11 +231,19 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
             const Seq* seqs = seq_scratch + d.seq_off;
             // records are read exactly once: stream them (evict-first) so that L2 keeps the frame's recent output instead
             Seq rec_next = lane < d.n_seq ? __ldcs(seqs + lane) : 0ull;
+#if CZB_EXEC_PF
+            Seq rec_next2 = lane + 32 < d.n_seq ? __ldcs(seqs + lane + 32) : 0ull;  // two chunks ahead: the next chunk's record is in registers when this one runs
+#endif
             for (uint32_t s0 = 0; s0 < d.n_seq; s0 += 32) {
                 const uint32_t i = s0 + lane;
                 const bool have = i < d.n_seq;
                 const Seq rec = rec_next;
+#if CZB_EXEC_PF
+                rec_next = rec_next2;
+                rec_next2 = i + 64 < d.n_seq ? __ldcs(seqs + i + 64) : 0ull;
+#else
                 if (i + 32 < d.n_seq) rec_next = __ldcs(seqs + i + 32);  // next chunk's record is in flight while this chunk executes
+#endif
                 uint32_t ll = 0, ml = 0, off = 1;
                 if (have) { ll = seq_ll(rec); ml = seq_ml(rec); off = off29_resolve(seq_off29(rec), h0, h1, h2); }
                 // warp prefix sums: literal offsets and output offsets (u32 cannot wrap: 32 * (131071 + 131074) < 2^32)
@@ -264,6 +275,20 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
                     const unsigned errm = __ballot_sync(0xFFFFFFFFu, err != CZS_OK);
                     if (errm) { status = __shfl_sync(0xFFFFFFFFu, err, __ffs(errm) - 1); break; }
                 }
+#if CZB_EXEC_PF
+                {   // L2 prefetch of the NEXT chunk's match sources that lie below this chunk (already in dst, possibly evicted to DRAM:
+                    // 4144 frames x 64 KiB in flight exceed the L2): no destination register, the line is in L2 when the next chunk loads it
+                    const bool have2 = i + 32 < d.n_seq;
+                    const uint32_t ll2 = have2 ? seq_ll(rec_next) : 0u, ml2 = have2 ? seq_ml(rec_next) : 0u;
+                    const uint32_t off2 = have2 ? off29_resolve(seq_off29(rec_next), h0, h1, h2) : 1u;
+                    uint32_t o2 = ll2 + ml2;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, o2, o); if ((int)lane >= o) o2 += a; }
+                    const uint32_t segM2 = span + o2 - ml2;  // relative to this chunk's base
+                    if (ml2 && off2 > segM2 && (uint64_t)off2 <= out + segM2)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(dst + out + segM2 - off2));
+                }
+#endif
 #if EXEC_TILE_PATH
                 if (span <= EXEC_TILE) {  // the common case: short segments, span of a few hundred bytes
                     exec_chunk_tile<false>(sm.tile, dst + out, lits, lit_rle, rle_byte, lane, ll, ml, off, my_lit, my_out, span, 0, NoWait{});
@@ -767,7 +792,7 @@ void launch_exec(const LaunchCtx& lc, const ExecSide& side, int sm_count, const 
         cudaStreamWaitEvent(side.stream, side.fork, 0);
         if (side.flow) {
             LaunchCtx ls{side.stream, lc.launches};
-            launch_exec_flow(ls, n_big_cls, descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first, side.resume ? side.resume + first : nullptr);
+            launch_exec_flow(ls, n_big_cls, descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first, side.resume ? side.resume + first : nullptr, side.flow_wide);
         } else {
             k_exec_big<<<n_big_cls, BIG_WARPS * 32, sizeof(BigSmem), side.stream>>>(descs + first, infos + first, rule, exec_order, blocks, lit_scratch, seq_scratch, results + first, side.resume ? side.resume + first : nullptr);
             ++*lc.launches;

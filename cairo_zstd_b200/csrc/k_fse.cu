@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 }
                 // :281-283; the no-RLE variant traps on the unwrap at :279 instead
                 if (EXACT) st = (st == CZS_OK && br.rem() < 0) ? short_status : st;
-                else trouble |= (uint32_t)br.rem();  // negative <=> bit 31
+                // (fast form: rem only ever decreases, so one look after the loop tells whether it went negative on the way)
             };
             // Four steps consume at most 356 bits, i.e. leave at most three 16-byte chunks behind: the ring is looked after
             // once per four steps (three always-issued cp.async) instead of once per step.
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             }
             for (; i + 1 < n_seq; i++) step(i, std::true_type{}, R1{}, QN{});
             step(i, std::false_type{}, R0{}, QN{});
-            if (!EXACT && (trouble >> 31)) st = CZS_NOT_DECODED;  // placeholder: the exact form decides
+            if (!EXACT && ((trouble >> 31) || br.rem() < 0)) st = CZS_NOT_DECODED;  // placeholder: the exact form decides
             if (st == CZS_OK && br.rem() > 0) st = CZS_SEQ_EXTRA_BITS;  // :292-296
         }
     }

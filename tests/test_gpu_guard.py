@@ -39,7 +39,7 @@ def _frames(corpus):
     return frames, caps
 
 
-@pytest.mark.parametrize("mode", ["default", "flow-forced", "big-forced"])
+@pytest.mark.parametrize("mode", ["default", "flow-forced", "flow-wide-forced", "big-forced"])
 def test_no_store_leaves_its_span_and_scratch_guards_stay_intact(corpus, monkeypatch, mode):
     import torch
     monkeypatch.setenv("CZB_GUARD", "1")
@@ -47,6 +47,8 @@ def test_no_store_leaves_its_span_and_scratch_guards_stay_intact(corpus, monkeyp
         monkeypatch.setenv("CZB_BIG_CLS", "0"); monkeypatch.setenv("CZB_BIG_SEQ_BYTES", "0")
     if mode == "big-forced":
         monkeypatch.setenv("CZB_BIG_FLOW", "0")
+    if mode == "flow-wide-forced":
+        monkeypatch.setenv("CZB_FLOW_WIDE", "1")
     ctx = czb.Context(0)
     frames, caps = _frames(corpus)
     n = len(frames)
