@@ -127,7 +127,7 @@ extern "C" void czb_context_destroy(czb_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p); cudaFree(ctx->guard_faults.p);
+    cudaFree(ctx->infos.p); cudaFree(ctx->totals_d.p); cudaFree(ctx->guard_faults.p); cudaFree(ctx->huf_big.p);
     for (int s = 0; s < 2; s++) {
         cudaFree(ctx->exec_order[s].p); cudaFree(ctx->huf_cls0[s].p); cudaFree(ctx->huf_cls1[s].p); cudaFree(ctx->huf_recs[s].p);
         cudaFree(ctx->blocks[s].p); cudaFree(ctx->huf_items[s].p); cudaFree(ctx->fse_items[s].p); cudaFree(ctx->lit[s].p);
@@ -232,6 +232,10 @@ static int decode_batch_impl(czb_context* ctx, const czb_frame_desc* descs, czb_
     if (plan && plan->n != n) { ctx->last_error = "plan was made for a different batch"; return CZS_BAD_ARGUMENT; }
     if ((rc = ensure(ctx, ctx->infos, n))) return rc;
     if ((rc = ensure(ctx, ctx->totals_d, kMaxWaves))) return rc;
+    if (!ctx->huf_big.p) {  // scratch for Huffman-weight FSE tables with an accuracy log above 9 (global memory, one warp at a time)
+        if ((rc = ensure(ctx, ctx->huf_big, huff_big_scratch_bytes()))) return rc;
+        CZB_CUDA(ctx, cudaMemsetAsync(ctx->huf_big.p, 0, 64, stream));  // the lock word
+    }
 
     // ---- plan: scan every frame, then size waves so that scratch fits the budget ----
     uint64_t W = std::min<uint64_t>((n + 127) / 128 * 128, ctx->wave_frames);
@@ -335,7 +339,7 @@ static int decode_batch_impl(czb_context* ctx, const czb_frame_desc* descs, czb_
         }
         CZB_CUDA(ctx, cudaMemsetAsync(ctx->counters[s].p, 0, sizeof(WaveCounters), stream));
         { ProfScope ps(ctx, stream, 1); launch_fill_blocks(lc, descs, ctx->infos.p, first, count, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->fse_items[s].p, ctx->counters[s].p, ctx->totals_d.p + w, ctx->exec_order[s].p, exact_classes ? 1 : 0, resume); }
-        if (!(flags & kFlagSizesOnly)) { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p, ctx->huf_recs[s].p, ctx->huf_cls0[s].p, ctx->huf_cls1[s].p); }
+        if (!(flags & kFlagSizesOnly)) { ProfScope ps(ctx, stream, 2); launch_huff(lc, descs + first, ctx->blocks[s].p, ctx->huf_items[s].p, ctx->counters[s].p, (uint32_t)t.n_huf, ctx->lit[s].p, ctx->huf_recs[s].p, ctx->huf_cls0[s].p, ctx->huf_cls1[s].p, ctx->huf_big.p); }
         { ProfScope ps(ctx, stream, 3); launch_fse(lc, descs + first, ctx->blocks[s].p, ctx->fse_items[s].p, ctx->counters[s].p, (uint32_t)t.n_fse, ctx->seq[s].p); }
         if (overlap) {
             CZB_CUDA(ctx, cudaEventRecord(ctx->ev_entropy[s], stream));

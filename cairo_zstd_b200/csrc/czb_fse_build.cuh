@@ -32,8 +32,10 @@ __device__ __forceinline__ uint32_t fse_entry_base(uint32_t e, uint32_t nb, uint
 // for Huffman weights, where the reference passes 100 (huff0_decoder.cairo:176) -- is still parsed to the end so
 // that every error the reference would raise is raised; if it parses cleanly CZS_UNSUPPORTED is returned with
 // bytes_read set (the caller may still prefer its own "used too many bytes" error).
+// probs32 (optional): receives the counts of an oversize description (accuracy log > FSE_MAX_LOG, where they do not fit 16 bits);
+// the function then returns CZS_OK for it and the caller builds a table in global memory (k_huff_prep, Huffman weights only).
 __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int max_log, int16_t* probs, int& n_probs, int& log,
-                                                 int& bytes_read) {
+                                                 int& bytes_read, int32_t* probs32 = nullptr) {
     FwdBits br{p, len, 0};
     uint32_t v;
     n_probs = 0;
@@ -57,7 +59,7 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
         else if (unchecked > mask) value = unchecked - low_threshold;
         else value = unchecked;
         const int prob = (int)value - 1;
-        if (n_probs < FSE_MAX_SYMBOLS && !oversize) probs[n_probs] = (int16_t)prob;
+        if (n_probs < FSE_MAX_SYMBOLS) { if (!oversize) probs[n_probs] = (int16_t)prob; else if (probs32) probs32[n_probs] = prob; }
         n_probs++;
         if (prob != 0) {
             counter += prob > 0 ? (uint32_t)prob : 1u;
@@ -65,7 +67,10 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
             for (;;) {
                 uint32_t skip;
                 if (!br.get(2, skip)) return CZS_FSE_GET_BITS_ERROR;
-                for (uint32_t k = 0; k < skip; k++) { if (n_probs < FSE_MAX_SYMBOLS && !oversize) probs[n_probs] = 0; n_probs++; }
+                for (uint32_t k = 0; k < skip; k++) {
+                    if (n_probs < FSE_MAX_SYMBOLS) { if (!oversize) probs[n_probs] = 0; else if (probs32) probs32[n_probs] = 0; }
+                    n_probs++;
+                }
                 if (skip != 3) break;
             }
         }
@@ -73,7 +78,67 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
     if (counter != sum) return CZS_FSE_PROBABILITY_COUNTER_MISMATCH;
     if (n_probs > 256) return CZS_FSE_TOO_MANY_SYMBOLS;
     bytes_read = (br.idx + 7) >> 3;
-    return oversize ? CZS_UNSUPPORTED : CZS_OK;
+    return (oversize && !probs32) ? CZS_UNSUPPORTED : CZS_OK;
+}
+
+// ---- oversize tables (accuracy log 10..20): only the Huffman-weight description can have one (the reference passes a limit of 100,
+// huff0_decoder.cairo:176; RFC 8878 allows 6, no encoder exceeds it).  Same construction as fse_build_table_warp with 32-bit
+// entries (symbol << 24 | next_state) and all arrays in global memory: one scratch area per context, taken by one warp at a time.
+constexpr int FSE_BIG_MAX_LOG = 20;  // 5 + 15: the largest value the 4-bit field can give (fse_decoder.cairo:265-276)
+struct FseBigScratch {
+    int lock;
+    int32_t probs[FSE_MAX_SYMBOLS];
+    uint32_t table[1u << FSE_BIG_MAX_LOG];
+    uint8_t rank_sym[1u << FSE_BIG_MAX_LOG];
+};
+__device__ __forceinline__ uint32_t fse_big_sym(uint32_t e) { return e >> 24; }
+__device__ __forceinline__ uint32_t fse_big_nbits(uint32_t e, uint32_t log) { return log - (31u - (uint32_t)__clz(e & 0xFFFFFFu)); }
+__device__ __forceinline__ uint32_t fse_big_base(uint32_t e, uint32_t nb, uint32_t log) { return ((e & 0xFFFFFFu) << nb) - (1u << log); }
+__device__ inline void fse_build_table_big(int32_t* probs, int n, int log, uint32_t* table, uint8_t* rank_sym) {
+    const unsigned lane = lane_id();
+    const int size = 1 << log;
+    int neg_idx = size, cum = 0;
+    for (int s0 = 0; s0 < n; s0 += 32) {
+        const int s = s0 + (int)lane;
+        const int pr = s < n ? probs[s] : 0;
+        const unsigned negm = __ballot_sync(0xFFFFFFFFu, pr == -1);
+        if (pr == -1) table[neg_idx - 1 - __popc(negm & lanemask_lt())] = ((uint32_t)s << 24) | 1u;
+        neg_idx -= __popc(negm);
+        const int pos = pr > 0 ? pr : 0;
+        int incl = pos;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += t; }
+        const int start = cum + incl - pos;
+        for (int q = 0; q < 32; q++) {  // a count can be 2^19 here: the whole warp fills each symbol's range
+            const int sq = __shfl_sync(0xFFFFFFFFu, start, q), pq = __shfl_sync(0xFFFFFFFFu, pos, q);
+            for (int k = (int)lane; k < pq; k += 32) rank_sym[sq + k] = (uint8_t)(s0 + q);
+        }
+        cum += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        if (pr == -1) probs[s] = 1;
+    }
+    __syncwarp();
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+    int rank_base = 0;
+    for (int j0 = 0; j0 < size; j0 += 32) {
+        const int j = j0 + (int)lane;
+        const int pos = (int)(((long long)j * step) & mask);
+        const bool ok = pos < neg_idx;
+        const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok);
+        if (ok) table[pos] = (uint32_t)rank_sym[rank_base + __popc(okm & lanemask_lt())] << 24;
+        rank_base += __popc(okm);
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < neg_idx; i0 += 32) {
+        const int i = i0 + (int)lane;
+        const bool ok = i < neg_idx;
+        const uint32_t s = ok ? (table[i] >> 24) : 0xFFFFu;
+        const unsigned same = __match_any_sync(0xFFFFFFFFu, s);
+        const int before = __popc(same & lanemask_lt());
+        if (ok) table[i] = (s << 24) | (uint32_t)(probs[s] + before);
+        __syncwarp();
+        if (ok && before == 0) probs[s] = probs[s] + __popc(same);
+        __syncwarp();
+    }
 }
 
 // Warp-cooperative table build.  probs[0..n) in shared memory (modified: becomes the running

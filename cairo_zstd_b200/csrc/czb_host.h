@@ -34,6 +34,7 @@ struct czb_context {
     DevBuf<czb::BlockDesc> blocks[2];
     DevBuf<uint32_t> huf_items[2], fse_items[2], huf_cls0[2], huf_cls1[2], exec_order[2];
     DevBuf<czb::HufRec> huf_recs[2];
+    DevBuf<uint8_t> huf_big;    // FseBigScratch: Huffman-weight FSE tables with accuracy log 10..20
     DevBuf<uint8_t> lit[2];
     DevBuf<czb::Seq> seq[2];
     cudaStream_t exec_stream = nullptr;

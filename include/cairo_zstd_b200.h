@@ -23,9 +23,9 @@
  *      src/huff0/huff0_decoder.cairo:302 reads `idx | 1 == 1`, i.e. (idx|1)==1; the reference's
  *      own fixtures pin only the RFC behaviour.
  *   2. CZS_UNSUPPORTED marks input the reference accepts but this build does not decode:
- *      a Huffman-weight FSE table with accuracy log > 9 (the reference passes a limit of 100,
- *      huff0_decoder.cairo:176; RFC 8878 allows 6) and frames whose output reaches 2^28 - 1 bytes.
- *      It never means "malformed".
+ *      frames whose output reaches 2^28 - 1 bytes.  It never means "malformed".
+ *      (Huffman-weight FSE tables with an accuracy log above 9 -- the reference passes a limit of
+ *      100, huff0_decoder.cairo:176 -- are decoded: tests/test_gpu_fuzz.py.)
  */
 #ifndef CAIRO_ZSTD_B200_H
 #define CAIRO_ZSTD_B200_H

@@ -107,9 +107,8 @@ typedef enum czs_status {
     /* Boundary-only codes (no reference counterpart) */
     CZS_DST_TOO_SMALL = 102,   /* caller's output span cannot hold the frame */
     CZS_UNSUPPORTED = 103,     /* NOT malformed input: accepted by the reference but outside this
-                                  build's limits (DESIGN.md "Limits"): a Huffman-weight FSE table
-                                  with accuracy log > 9 (src/huff0/huff0_decoder.cairo:176 passes a
-                                  limit of 100), or a frame whose output reaches 2^28 - 1 bytes */
+                                  build's limit (DESIGN.md "Limits"): a frame whose output reaches
+                                  2^28 - 1 bytes (sequence records keep a 28-bit offset) */
     CZS_CUDA_ERROR = 104,      /* CUDA runtime failure; see czb_last_error() */
     CZS_BAD_ARGUMENT = 105,
     CZS_NOT_DECODED = 106      /* result slot never written (internal) */

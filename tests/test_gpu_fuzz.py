@@ -2,10 +2,11 @@
 
 Seeded mutations (truncation, bit flip, byte stomp, header stomp) of corpus and synthetic frames.  The leaf status of
 every frame must be IDENTICAL to the oracle's -- the reference's error order: block order, then literals header ->
-literals -> sequences header -> tables -> sequences -> execution (src/decoding/block_decoder.cairo:139-235) -- except
-for the one enumerated limit of this build: CZS_UNSUPPORTED, returned where the reference would go on with a
-Huffman-weight FSE table of accuracy log > 9 (src/huff0/huff0_decoder.cairo:176 passes a limit of 100) or an output
-of >= 2^28 bytes (include/czstd_status.h, DESIGN.md "Limits").  Outputs of frames that still decode must be identical too."""
+literals -> sequences header -> tables -> sequences -> execution (src/decoding/block_decoder.cairo:139-235).  The one
+enumerated limit of this build, CZS_UNSUPPORTED for a frame whose output reaches 2^28 - 1 bytes (include/czstd_status.h,
+DESIGN.md "Limits"), cannot be reached with these capacities, so no exception is made.  (Huffman-weight FSE tables with an
+accuracy log above 9, the other round-1 limit, are decoded now: see the last test.)  Outputs of frames that still decode
+must be identical too."""
 import numpy as np
 import pytest
 
@@ -49,14 +50,46 @@ def _mutants(corpus, seed):
 def test_mutated_frames_give_the_oracles_leaf_status(corpus, seed):
     frames, caps = _mutants(corpus, seed)
     outs, res = gpu_decode(frames, caps, 0)
-    differ, unsupported = [], 0
+    differ = []
     for i, f in enumerate(frames):
         st, want, _ = O.decode_frame(f, dst_cap=caps[i])
         g = res[i].status
-        if g == CZS_UNSUPPORTED and st != CZS_UNSUPPORTED:
-            unsupported += 1  # the enumerated limit of this build (see the module docstring)
-            continue
         if st != g or (st == 0 and outs[i] != want):
             differ.append((i, czb.status_name(st), czb.status_name(g)))
     assert not differ, f"{len(differ)} of {len(frames)} differ: {differ[:12]}"
-    assert unsupported <= max(3, len(frames) // 100), f"{unsupported} frames hit CZS_UNSUPPORTED"
+    assert all(r.status != CZS_UNSUPPORTED for r in res)
+
+
+def test_huffman_weight_tables_with_accuracy_log_above_9(corpus):
+    """The reference builds the FSE table of a Huffman weight description with whatever accuracy log its 4-bit field gives (5..20:
+    src/huff0/huff0_decoder.cairo:176 passes a limit of 100).  Tables above log 9 do not fit the shared-memory format; they are built
+    in global memory (k_huff_prep, FseBigScratch).  Hand-assembled frames with such tables and random weight / literal bitstreams:
+    whatever the oracle says (mostly weight errors, since random bits rarely give a complete Huffman code), the GPU says the same,
+    and the big-table path is really taken (the description parses and the error, if any, comes from after the table build)."""
+    import handmade as H
+    rng = np.random.default_rng(2026)
+    frames = []
+    for k in range(400):
+        log = int(rng.choice([10, 10, 11, 12, 13, 14, 16, 20]))
+        nsym = int(rng.integers(2, 9))          # weight values 0 .. nsym-1
+        total = 1 << log
+        cuts = np.sort(rng.choice(np.arange(1, total), size=nsym - 1, replace=False))
+        probs = np.diff(np.concatenate([[0], cuts, [total]])).astype(int).tolist()
+        if k % 5 == 0 and probs[-1] > 2:        # some "less than one" symbols and a zero run
+            probs[-1] -= 2
+            probs += [0, 0, -1, -1]
+        ws = bytes(rng.integers(0, 256, size=int(rng.integers(1, 24)), dtype=np.uint8).tolist()[:-1] + [int(rng.integers(1, 256))])
+        hs = bytes(rng.integers(0, 256, size=int(rng.integers(1, 40)), dtype=np.uint8).tolist()[:-1] + [int(rng.integers(1, 256))])
+        frames.append(H.frame_with_weight_table(log, probs, ws, hs, int(rng.integers(1, 300))))
+    caps = [1024] * len(frames)
+    outs, res = gpu_decode(frames, caps, 0)
+    FSE_DESC_ERRORS = {36, 37, 38, 39, 40}      # errors of read_probabilities: the description itself did not parse
+    past_table = 0
+    for i, f in enumerate(frames):
+        st, want, _ = O.decode_frame(f, dst_cap=caps[i])
+        assert res[i].status == st, (i, czb.status_name(st), czb.status_name(res[i].status))
+        assert st != CZS_UNSUPPORTED
+        if st == 0:
+            assert outs[i] == want
+        past_table += st not in FSE_DESC_ERRORS
+    assert past_table >= len(frames) // 2, past_table

@@ -299,9 +299,9 @@ def test_truncations_and_bit_flips_match_oracle_status(corpus):
         if (st == 0) != (res[k].status == 0) or (st == 0 and outs[k] != want):
             mism.append((k, czb.status_name(st), czb.status_name(res[k].status)))
     assert not mism, mism[:10]
-    # leaf status codes are identical, except for the enumerated limit of this build (CZS_UNSUPPORTED = 103, see tests/test_gpu_fuzz.py)
+    # leaf status codes are identical (see also tests/test_gpu_fuzz.py)
     diff = [(k, czb.status_name(O.decode_frame(f, dst_cap=caps[k])[0]), czb.status_name(res[k].status)) for k, f in enumerate(frames)
-            if O.decode_frame(f, dst_cap=caps[k])[0] != res[k].status and res[k].status != 103]
+            if O.decode_frame(f, dst_cap=caps[k])[0] != res[k].status]
     assert not diff, diff[:10]
 
 
