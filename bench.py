@@ -469,9 +469,10 @@ def config5_sharded(args, ctx, torch, dev, dist, rank, world):
     import cairo_zstd_b200 as czb
     from cairo_zstd_b200 import workloads as W
     frames, origs = W.config5_mixed_sizes(512, hi=4 << 20)   # seeded: identical on every rank
-    # 65 536 frames (36.6 GB decoded): large enough that at N = 8 a rank's share is still many times its largest frame -- a frame is
+    # 131 072 frames (73 GB decoded): large enough that at N = 8 a rank's share is still many times its largest frame -- a frame is
     # one sequential stream (a 4 MiB frame takes ~10 ms however few others there are), so a batch of a few GB cannot scale
-    n0, reps = len(frames), 128
+    # (65 536 frames: 174.6 GB/s on one GPU, 1134 on eight = 0.81; 8192 frames: 155 -> 188 on two)
+    n0, reps = len(frames), 256
     n = n0 * reps
     cost = np.array([len(f) + len(o) for f, o in zip(frames, origs)], dtype=np.int64)
     cost_all = cost[np.arange(n) % n0]
@@ -489,7 +490,7 @@ def config5_sharded(args, ctx, torch, dev, dist, rank, world):
             "shard_cost_bytes": [int(x) for x in load],
             "imbalance": max(load) / (sum(load) / world) - 1.0,
             "partition": "czb_partition_frames (C ABI): largest first by compressed + decoded bytes",
-            "workload": "mixed sizes: 65536 frames of 1 KiB..4 MiB log-uniform (512 distinct x 128), the same batch at every N",
+            "workload": "mixed sizes: 131072 frames of 1 KiB..4 MiB log-uniform (512 distinct x 256), the same batch at every N",
             "verified": "status, size and device XXH64 == trailer for every frame of every shard"}
 
 

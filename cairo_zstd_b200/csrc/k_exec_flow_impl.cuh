@@ -27,6 +27,7 @@ struct FlowSmem {
     uint32_t next_chunk, head;            // claim counter; first chunk not retired yet
     uint32_t err_chunk;                   // smallest failing chunk number of the batch, NONE32 if none
     int32_t err_status;
+    uint32_t abort;                       // a wait loop gave up (flow_abort): everybody leaves, the frame fails
     __align__(16) uint8_t long_tile[EXEC_TILE + 48];
 };
 
@@ -107,18 +108,19 @@ __device__ unsigned long long czb_flow_clk[24];
 #define FCNT(k, v) do { } while (0)
 #endif
 
-// Debug aid (-DCZB_FLOW_WATCHDOG): a wait loop that spins too long records what it waits for in czb_flow_wd (read back with
-// czb_debug_flow_watchdog) and LEAVES the loop, so that the kernel ends instead of hanging.
+// Safety net: the wait loops below cannot spin for ever.  A loop that has spun FLOW_SPIN_LIMIT times (tens of milliseconds; a healthy
+// wait is microseconds) records what it was waiting for in czb_flow_wd (czb_debug_flow_watchdog), raises the CTA's abort flag -- every
+// wait loop of the CTA leaves when it sees it -- and the frame fails with CZS_PANIC_INTERNAL instead of hanging the GPU.
 __device__ unsigned int czb_flow_wd[16];
-#ifdef CZB_FLOW_WATCHDOG
-#define FWD_DECL uint32_t wd_ = 0
-#define FWD(code, a, b, c2, d2, e, f2, g, h) { if (++wd_ > (1u << 20)) { if (atomicCAS(&czb_flow_wd[0], 0u, (unsigned)(code)) == 0u) { \
-    czb_flow_wd[1] = blockIdx.x; czb_flow_wd[2] = threadIdx.x >> 5; czb_flow_wd[3] = (a); czb_flow_wd[4] = (b); czb_flow_wd[5] = (c2); czb_flow_wd[6] = (d2); \
-    czb_flow_wd[7] = (e); czb_flow_wd[8] = (f2); czb_flow_wd[9] = (g); czb_flow_wd[10] = (h); } break; } }
-#else
-#define FWD_DECL do { } while (0)
-#define FWD(code, a, b, c2, d2, e, f2, g, h) { }
-#endif
+constexpr uint32_t FLOW_SPIN_LIMIT = 1u << 21;
+__device__ __forceinline__ void flow_abort(uint32_t* abort_flag, unsigned code, uint32_t a, uint32_t b, uint32_t c2, uint32_t d2, uint32_t e, uint32_t f2,
+                                           uint32_t g, uint32_t h) {
+    if (atomicCAS(&czb_flow_wd[0], 0u, code) == 0u) {
+        czb_flow_wd[1] = blockIdx.x; czb_flow_wd[2] = threadIdx.x >> 5; czb_flow_wd[3] = a; czb_flow_wd[4] = b; czb_flow_wd[5] = c2;
+        czb_flow_wd[6] = d2; czb_flow_wd[7] = e; czb_flow_wd[8] = f2; czb_flow_wd[9] = g; czb_flow_wd[10] = h;
+    }
+    atomicExch(abort_flag, 1u);
+}
 
 struct FlowWin {
     uint8_t* win;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, FLOW_P_MIN_CTAS) k_exec_flow(
                     if (lane == 0) {
                         sm.chunk_lit[nb] = sat(cl); sm.chunk_out[nb] = sat(co);
                         sm.next_chunk = 0; sm.head = 0; sm.retired_out = batch_out0; sm.win_lo = batch_out0;
-                        sm.err_chunk = NONE32; sm.err_status = CZS_OK;
+                        sm.err_chunk = NONE32; sm.err_status = CZS_OK; sm.abort = 0u;
                     }
                 }
                 __syncthreads();
@@ -300,7 +302,13 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, FLOW_P_MIN_CTAS) k_exec_flow(
 
                     if (errm || is_long) {
                         // ---- alone: everything before this chunk has retired ----
-                        if (lane == 0) { FWD_DECL; while (vld(&sm.head) != c) { flow_try_retire(sm, nb, batch_out0); __nanosleep(64); FWD(1, c, vld(&sm.head), vld(&sm.next_chunk), vld(&sm.retired_out), vld(&sm.done[vld(&sm.head) % FLOW_NSLOT]), nb, 0, 0); } }
+                        if (lane == 0) {
+                            uint32_t spins = 0;
+                            while (vld(&sm.head) != c && !vld(&sm.abort)) {
+                                flow_try_retire(sm, nb, batch_out0); __nanosleep(64);
+                                if (++spins > FLOW_SPIN_LIMIT) flow_abort(&sm.abort, 1u, c, vld(&sm.head), vld(&sm.next_chunk), vld(&sm.retired_out), vld(&sm.done[vld(&sm.head) % FLOW_NSLOT]), nb, 0u, 0u);
+                            }
+                        }
                         __syncwarp();
                         flow_fence();
                         FCLK(3); FCNT(17, 1);
@@ -362,13 +370,14 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, FLOW_P_MIN_CTAS) k_exec_flow(
                     // and a long chunk before this one must have retired (it moves win_lo)
                     if (lane == 0) {
                         const uint32_t pl = sm.prev_long[c];
-                        FWD_DECL;
+                        uint32_t spins = 0;
                         for (;;) {
                             const uint32_t hd = vld(&sm.head);
                             if (O + span <= vld(&sm.retired_out) + FLOW_INFLIGHT && c - hd < FLOW_NSLOT && (pl == 0xFFFFu || hd > pl)) break;
+                            if (vld(&sm.abort)) break;
                             flow_try_retire(sm, nb, batch_out0);
                             __nanosleep(32);
-                            FWD(2, c, hd, vld(&sm.next_chunk), vld(&sm.retired_out), vld(&sm.done[hd % FLOW_NSLOT]), nb, O, span);
+                            if (++spins > FLOW_SPIN_LIMIT) flow_abort(&sm.abort, 2u, c, hd, vld(&sm.next_chunk), vld(&sm.retired_out), vld(&sm.done[hd % FLOW_NSLOT]), nb, O, span);
                         }
                     }
                     __syncwarp();
@@ -410,10 +419,12 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, FLOW_P_MIN_CTAS) k_exec_flow(
                     // matches still pending after k rounds are taken in sequence order by the whole warp instead (measured slower:
                     // an in-order pass makes every later match of the chunk wait behind the first one that is not ready).
                     bool pending = ml > 0;
+                    uint32_t idle_spins = 0;
                     for (uint32_t round = 0; __any_sync(0xFFFFFFFFu, pending); round++) {
-                        uint32_t r_now = 0;
-                        if (lane == 0) r_now = vld(&sm.retired_out);
+                        uint32_t r_now = 0, ab = 0;
+                        if (lane == 0) { r_now = vld(&sm.retired_out); ab = vld(&sm.abort); }
                         r_now = __shfl_sync(0xFFFFFFFFu, r_now, 0);
+                        if (__shfl_sync(0xFFFFFFFFu, ab, 0)) break;  // somebody gave up: the frame fails, nothing here matters any more
                         bool ready = false;
                         if (pending) {
                             if (s_end <= lo_abs || s_end <= r_now) ready = true;
@@ -422,7 +433,10 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, FLOW_P_MIN_CTAS) k_exec_flow(
                         }
                         const unsigned rm = __ballot_sync(0xFFFFFFFFu, ready);
                         if (!rm) {
-                            if (lane == 0) { flow_try_retire(sm, nb, batch_out0); __nanosleep(32); }
+                            if (lane == 0) {
+                                flow_try_retire(sm, nb, batch_out0); __nanosleep(32);
+                                if (++idle_spins > FLOW_SPIN_LIMIT) flow_abort(&sm.abort, 3u, c, vld(&sm.head), vld(&sm.next_chunk), r_now, O, span, lo_abs, 0u);
+                            }
                             __syncwarp();
                             FCLK(7); FCNT(18, 1);
                             continue;
@@ -493,6 +507,7 @@ __global__ void __launch_bounds__(FLOW_WARPS * 32, FLOW_P_MIN_CTAS) k_exec_flow(
                 __syncthreads();  // everything of the batch is complete in dst and visible to the whole CTA
                 FCLK(15);
                 if (sm.err_chunk != NONE32) { status = sm.err_status; failed = true; }
+                if (sm.abort) { status = CZS_PANIC_INTERNAL; failed = true; }  // a wait loop gave up (flow_abort): never seen; a bug, not an input error
                 lit_total += lit_batch; out_total += out_batch;
                 __syncthreads();
             }  // batch loop
