@@ -43,6 +43,13 @@ class ShardStat(C.Structure):
                 ("bytes_out", C.c_uint64), ("ms", C.c_double)]
 
 
+class DictionaryInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("id", C.c_uint32), ("huf_bytes", C.c_uint32), ("of_bytes", C.c_uint32), ("ml_bytes", C.c_uint32),
+                ("ll_bytes", C.c_uint32), ("huf_max_bits", C.c_uint32), ("n_weights", C.c_uint32), ("of_log", C.c_uint32),
+                ("ml_log", C.c_uint32), ("ll_log", C.c_uint32), ("offset_hist", C.c_uint32 * 3), ("table_hash", C.c_uint32),
+                ("content_off", C.c_uint64), ("content_len", C.c_uint64)]
+
+
 class DebugBlock(C.Structure):
     _fields_ = [
         ("frame", C.c_uint32), ("block_type", C.c_uint8), ("lit_type", C.c_uint8), ("n_streams", C.c_uint8), ("modes", C.c_uint8),
@@ -78,7 +85,7 @@ EXPORTS = [
     "czb_debug_last_wave_counts", "czb_debug_copy_blocks", "czb_debug_copy_literals", "czb_debug_copy_sequences",
     "czb_kernel_launches", "czb_profile_enable", "czb_profile_collect", "czs_status_name",
     "czb_split_frames_host", "czb_split_frames_device", "czb_frame_sizes_device", "czb_frame_sizes_host",
-    "czb_plan_batch_device", "czb_plan_destroy", "czb_decode_batch_device_planned", "czb_debug_fd_device_work", "czb_debug_guard_faults", "czb_debug_flow_watchdog", "czb_partition_frames", "czb_multi_create", "czb_multi_destroy", "czb_decode_batch_multi", "czb_multi_last_error",
+    "czb_dictionary_parse_host", "czb_plan_batch_device", "czb_plan_destroy", "czb_decode_batch_device_planned", "czb_debug_fd_device_work", "czb_debug_guard_faults", "czb_debug_flow_watchdog", "czb_partition_frames", "czb_multi_create", "czb_multi_destroy", "czb_decode_batch_multi", "czb_multi_last_error",
 ]
 
 _lib = None
@@ -132,6 +139,7 @@ def load_library():
     L.czb_kernel_launches.restype = u64
     L.czb_profile_enable.argtypes = [vp, C.c_int]
     L.czb_profile_collect.argtypes = [vp, P(C.c_double), P(u64)]
+    L.czb_dictionary_parse_host.argtypes = [vp, C.c_char_p, u64, P(DictionaryInfo)]
     L.czb_plan_batch_device.argtypes = [vp, vp, u64, vp, P(vp)]
     L.czb_plan_destroy.argtypes = [vp]
     L.czb_decode_batch_device_planned.argtypes = [vp, vp, vp, vp, u64, u32, vp]
@@ -309,6 +317,12 @@ class Context:
         so = src_off.ctypes.data if hasattr(src_off, "ctypes") else C.addressof(src_off)
         do = dst_off.ctypes.data if hasattr(dst_off, "ctypes") else C.addressof(dst_off)
         self._check(self._L.czb_decode_batch_host_packed(self._h, src_base, so, dst_base, do, results_ptr, n, flags))
+
+    def dictionary_parse(self, dict_bytes: bytes) -> DictionaryInfo:
+        """czb_dictionary_parse_host: Dictionary::decode_dict (dictionary.cairo:35-90) on the device; status inside."""
+        info = DictionaryInfo()
+        self._L.czb_dictionary_parse_host(self._h, dict_bytes, len(dict_bytes), C.byref(info))
+        return info
 
     def guard_faults(self) -> int:
         """CZB_GUARD=1 contexts: guard bytes behind the scratch buffers found overwritten so far (0 = clean)."""

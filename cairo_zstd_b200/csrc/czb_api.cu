@@ -691,6 +691,29 @@ extern "C" const char* czb_multi_last_error(const czb_multi* m, int shard) {
     return (m && shard >= 0 && (size_t)shard < m->ctxs.size()) ? czb_last_error(m->ctxs[shard]) : "bad shard";
 }
 
+// ---- dictionaries: the reference's parse, mirrored (row f4) ---------------------------------------
+extern "C" int czb_dictionary_parse_host(czb_context* ctx, const uint8_t* dict, uint64_t len, czb_dictionary_info* out) {
+    if (!ctx || !out || (!dict && len)) return CZS_BAD_ARGUMENT;
+    memset(out, 0, sizeof *out);
+    CZB_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->h_src[0], len + 64))) return rc;
+    if ((rc = ensure(ctx, ctx->h_results, 4))) return rc;  // reused as the output slot (sizeof(czb_dictionary_info) <= 4 results)
+    static_assert(sizeof(czb_dictionary_info) <= 4 * sizeof(czb_frame_result), "output slot");
+    cudaStream_t st = ctx->compute;
+    if (ctx->scratch_in_use) CZB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_scratch_free, 0));
+    if (!ctx->huf_big.p) {
+        if ((rc = ensure(ctx, ctx->huf_big, huff_big_scratch_bytes()))) return rc;
+        CZB_CUDA(ctx, cudaMemsetAsync(ctx->huf_big.p, 0, 64, st));
+    }
+    if (len) CZB_CUDA(ctx, cudaMemcpyAsync(ctx->h_src[0].p, dict, len, cudaMemcpyHostToDevice, st));
+    LaunchCtx lc{st, &ctx->launches};
+    launch_dict_parse(lc, ctx->h_src[0].p, len, reinterpret_cast<czb_dictionary_info*>(ctx->h_results.p), ctx->huf_big.p);
+    CZB_CUDA(ctx, cudaMemcpyAsync(out, ctx->h_results.p, sizeof *out, cudaMemcpyDeviceToHost, st));
+    CZB_CUDA(ctx, cudaStreamSynchronize(st));
+    return out->status;
+}
+
 // ---- header pre-pass (CPU only) ---------------------------------------------------------------
 extern "C" int czb_frame_header_info_host(const uint8_t* src, uint64_t src_len, czb_frame_header_info* out) {
     if (!out || (!src && src_len)) return CZS_BAD_ARGUMENT;
@@ -806,7 +829,7 @@ extern "C" const char* czs_status_name(int s) {
         N(CZS_SEQ_EXTRA_PADDING) N(CZS_SEQ_UNSUPPORTED_OFFSET) N(CZS_SEQ_NOT_ENOUGH_BYTES_FOR_NUM_SEQUENCES) N(CZS_SEQ_EXTRA_BITS)
         N(CZS_SEQ_GET_BITS_ERROR) N(CZS_MISSING_BYTE_FOR_RLE_LL_TABLE) N(CZS_MISSING_BYTE_FOR_RLE_OF_TABLE)
         N(CZS_MISSING_BYTE_FOR_RLE_ML_TABLE) N(CZS_EXEC_NOT_ENOUGH_BYTES_FOR_SEQUENCE) N(CZS_EXEC_ZERO_OFFSET)
-        N(CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY) N(CZS_OFFSET_TOO_BIG) N(CZS_PANIC_TRUNCATED) N(CZS_PANIC_INTERNAL) N(CZS_DST_TOO_SMALL)
+        N(CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY) N(CZS_OFFSET_TOO_BIG) N(CZS_DICT_BAD_MAGIC) N(CZS_PANIC_TRUNCATED) N(CZS_PANIC_INTERNAL) N(CZS_DST_TOO_SMALL)
         N(CZS_UNSUPPORTED) N(CZS_CUDA_ERROR) N(CZS_BAD_ARGUMENT) N(CZS_NOT_DECODED)
 #undef N
     }

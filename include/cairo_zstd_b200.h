@@ -187,6 +187,27 @@ int czb_decode_batch_multi(czb_multi* m, const czb_frame_desc* descs, czb_frame_
                            uint32_t flags, czb_shard_stat* stats);
 const char* czb_multi_last_error(const czb_multi* m, int shard);
 
+/* ---- dictionaries -------------------------------------------------- */
+/* Dictionary::decode_dict (src/decoding/dictionary.cairo:35-90): the reference PARSES a dictionary -- magic 0xEC30A437, id, a
+ * Huffman table, the OF / ML / LL FSE tables (max logs 8 / 9 / 9), three repeat offsets, the content -- and never applies it
+ * (frame_decoder.cairo:73 passes an empty dictionary; README: "Dictionary support" is not done).  This entry point mirrors the
+ * parse on the device with the kernels' own table builders and reports what the reference's Dictionary struct would hold.
+ * table_hash = FNV-1a (32 bit) over the four decoding tables' entries in index order: Huffman `symbol | num_bits << 8`, then OF, ML,
+ * LL `symbol | num_bits << 8 | base_line << 12` (FSE symbols above 63 -- invalid codes for every stream -- count as 63).
+ * Errors: CZS_DICT_BAD_MAGIC, the HuffmanTableError / FSETableError leaf codes, CZS_PANIC_TRUNCATED where the reference's
+ * `.expect()` would trap.  dict is a HOST pointer. */
+typedef struct czb_dictionary_info {
+    int32_t status;
+    uint32_t id;
+    uint32_t huf_bytes, of_bytes, ml_bytes, ll_bytes; /* bytes each table description occupies */
+    uint32_t huf_max_bits, n_weights;
+    uint32_t of_log, ml_log, ll_log;
+    uint32_t offset_hist[3];
+    uint32_t table_hash;
+    uint64_t content_off, content_len;                /* dict_content = dict[content_off .. content_off + content_len) */
+} czb_dictionary_info;
+int czb_dictionary_parse_host(czb_context* ctx, const uint8_t* dict, uint64_t len, czb_dictionary_info* out);
+
 /* ---- FrameDecoder handle (1:1 mirror of src/frame_decoder.cairo) --------------------- */
 typedef struct czb_frame_decoder czb_frame_decoder;
 

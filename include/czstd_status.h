@@ -95,6 +95,9 @@ typedef enum czs_status {
     CZS_NOT_ENOUGH_BYTES_IN_DICTIONARY = 53,         /* :69-75 */
     CZS_OFFSET_TOO_BIG = 54,                         /* :91-93 */
 
+    /* DictionaryDecodeError -- src/decoding/dictionary.cairo:21-25 (FSETableError / HuffmanTableError reuse the codes above) */
+    CZS_DICT_BAD_MAGIC = 55,                         /* :47-49 */
+
     /* Reference PANICS flattened (process abort in Cairo) */
     CZS_PANIC_TRUNCATED = 100, /* slice/index past the end of the source span:
                                   src/utils/byte_array.cairo:20-21 reached from

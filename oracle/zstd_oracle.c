@@ -1165,6 +1165,55 @@ int32_t oracle_fd_decode_from_to(oracle_fd* fd, const uint8_t* src, size_t src_l
 void oracle_fd_getters(const oracle_fd* fd, oracle_result* res) { memset(res, 0, sizeof *res); fd_fill_result(fd, res); }
 
 /* ------------------------------------------------------------------------- */
+/* Dictionary::decode_dict (src/decoding/dictionary.cairo:35-90): parsed, never applied by the reference  */
+/* (frame_decoder.cairo:73 passes an empty dictionary).                                                   */
+/* ------------------------------------------------------------------------- */
+static uint32_t fnv_step(uint32_t h, uint32_t v) { return (h ^ v) * 16777619u; }
+int oracle_dict_decode(const uint8_t* raw, size_t len, oracle_dict_info* out) {
+    memset(out, 0, sizeof *out);
+    out->offset_hist[0] = 2; out->offset_hist[1] = 4; out->offset_hist[2] = 8; /* :43 */
+    if (len < 8) return CZS_PANIC_TRUNCATED;            /* word_u32_le(..).expect :46, :51 */
+    uint32_t magic = rd32le(raw);
+    if (magic != 0xEC30A437u) return CZS_DICT_BAD_MAGIC; /* :47-49 */
+    out->id = rd32le(raw + 4);
+    slice_t t = {raw + 8, len - 8};
+    uint32_t h = 2166136261u;
+    {   /* Huffman table :56-61 */
+        huf_table_t* ht = (huf_table_t*)malloc(sizeof *ht); huf_table_init(ht);
+        size_t used = 0;
+        int e = huf_build_decoder(ht, t, 0, &used);
+        if (!e) {
+            out->huf_bytes = (uint32_t)used; out->huf_max_bits = ht->max_num_bits; out->n_weights = ht->n_weights;
+            for (uint32_t i = 0; i < ht->decode_len; i++) h = fnv_step(h, (uint32_t)ht->decode[i].symbol | ((uint32_t)ht->decode[i].num_bits << 8));
+        }
+        fse_table_free(&ht->fse); free(ht);
+        if (e) return e;
+        t.p += used; t.len -= used;
+    }
+    const uint8_t max_log[3] = {8, 9, 9}; /* OF, ML, LL :63-79 */
+    uint32_t* bytes_out[3] = {&out->of_bytes, &out->ml_bytes, &out->ll_bytes};
+    uint32_t* log_out[3] = {&out->of_log, &out->ml_log, &out->ll_log};
+    for (int k = 0; k < 3; k++) {
+        fse_table_t ft; fse_table_init(&ft);
+        size_t used = 0;
+        int e = fse_build_decoder(&ft, t, max_log[k], &used);
+        if (!e) {
+            *bytes_out[k] = (uint32_t)used; *log_out[k] = ft.accuracy_log;
+            for (uint32_t i = 0; i < ft.decode_len; i++)
+                h = fnv_step(h, (uint32_t)(ft.decode[i].symbol > 63 ? 63 : ft.decode[i].symbol) | ((uint32_t)ft.decode[i].num_bits << 8) | (ft.decode[i].base_line << 12));
+        }
+        fse_table_free(&ft);
+        if (e) return e;
+        t.p += used; t.len -= used;
+    }
+    if (t.len < 12) return CZS_PANIC_TRUNCATED;          /* word_u32_le(..).expect :82-84 */
+    out->offset_hist[0] = rd32le(t.p); out->offset_hist[1] = rd32le(t.p + 4); out->offset_hist[2] = rd32le(t.p + 8);
+    out->content_off = (uint64_t)(t.p + 12 - raw); out->content_len = t.len - 12;
+    out->table_hash = h;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
 /* multi-threaded batch (CPU baseline: one frame per task)                    */
 /* ------------------------------------------------------------------------- */
 typedef struct {

@@ -118,6 +118,18 @@ int oracle_fse_build_decoder(const uint8_t* p, size_t len, uint8_t max_log, uint
 int oracle_huf_build_decoder(const uint8_t* p, size_t len, uint32_t flags, uint8_t* symbol,
                              uint8_t* num_bits, uint32_t* max_num_bits, size_t* bytes_read,
                              uint8_t* weights_out /*>=258*/, uint32_t* n_weights);
+/* Dictionary::decode_dict (src/decoding/dictionary.cairo:35-90).  table_hash: FNV-1a over the four decoding tables' entries in
+ * index order (Huffman: symbol | num_bits << 8; FSE OF, ML, LL: symbol | num_bits << 8 | base_line << 12). */
+typedef struct {
+    uint32_t id;
+    uint32_t huf_bytes, of_bytes, ml_bytes, ll_bytes;
+    uint32_t huf_max_bits, n_weights;
+    uint32_t of_log, ml_log, ll_log;
+    uint32_t offset_hist[3];
+    uint32_t table_hash;
+    uint64_t content_off, content_len;
+} oracle_dict_info;
+int oracle_dict_decode(const uint8_t* raw, size_t len, oracle_dict_info* out);
 /* do_offset_history (sequence_execution.cairo:85-129) */
 uint32_t oracle_offset_history(uint32_t offset_value, uint32_t lit_len, uint32_t hist[3]);
 

@@ -30,6 +30,13 @@ class OracleResult(C.Structure):
     ]
 
 
+class DictInfo(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("huf_bytes", C.c_uint32), ("of_bytes", C.c_uint32), ("ml_bytes", C.c_uint32), ("ll_bytes", C.c_uint32),
+                ("huf_max_bits", C.c_uint32), ("n_weights", C.c_uint32), ("of_log", C.c_uint32), ("ml_log", C.c_uint32),
+                ("ll_log", C.c_uint32), ("offset_hist", C.c_uint32 * 3), ("table_hash", C.c_uint32), ("content_off", C.c_uint64),
+                ("content_len", C.c_uint64)]
+
+
 class BlockTrace(C.Structure):
     _fields_ = [
         ("block_type", C.c_uint8),
@@ -101,6 +108,7 @@ def lib():
                                                C.POINTER(C.c_size_t), u8p, C.POINTER(C.c_uint32)]
         L.oracle_offset_history.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.oracle_offset_history.restype = C.c_uint32
+        L.oracle_dict_decode.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(DictInfo)]
         L.oracle_fd_new.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_uint32, C.POINTER(C.c_int32)]
         L.oracle_fd_new.restype = C.c_void_p
         L.oracle_fd_reset.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
