@@ -4,7 +4,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libcairo_zstd_b200.so")
+_LIB_PATH = os.environ.get("CZB_LIB") or os.path.join(_HERE, "libcairo_zstd_b200.so")  # CZB_LIB: a variant build, for A/B measurements
 _INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 FLAG_VERIFY_CHECKSUM = 1

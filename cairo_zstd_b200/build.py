@@ -20,15 +20,20 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, lib_out=None, objdir="build"):
+    """lib_out / objdir: build a variant (other -D flags through CZB_NVCC_FLAGS) next to the product library, for A/B runs:
+    CZB_LIB=<lib_out> makes api.load_library() pick it up."""
+    lib_out = lib_out or os.environ.get("CZB_LIB_OUT") or LIB
+    if lib_out != LIB:
+        force, objdir = True, "build/" + os.path.basename(lib_out).replace(".so", "")
     if not (force or stale()):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, objdir), exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        o = os.path.join(HERE, objdir, s.replace(".cu", ".o"))
         objs.append(o)
         cmd = [nvcc] + NVCC_FLAGS + os.environ.get("CZB_NVCC_FLAGS", "").split() + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -40,13 +45,13 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             fail = True
     text = "\n".join(log)
-    open(os.path.join(HERE, "build", "ptxas.log"), "w").write(text)
+    open(os.path.join(HERE, objdir, "ptxas.log"), "w").write(text)
     if fail or verbose:
         print(text, file=sys.stderr if fail else sys.stdout)
     if fail:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
-    return LIB
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_out] + objs)
+    return lib_out
 
 
 if __name__ == "__main__":

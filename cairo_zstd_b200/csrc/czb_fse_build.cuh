@@ -8,7 +8,7 @@
 //     base_line = (next_state << num_bits) - (1 << log)
 // where next_state = prob[symbol] + (number of earlier cells holding the same symbol).  This is
 // algebraically the reference's calc_baseline_and_numbits(table_size, prob, k) (checked for every
-// (log, prob, k) in tests/test_gpu_units.py) and halves the shared-memory footprint versus storing
+// (log, prob, k) in tests/test_formulas.py) and halves the shared-memory footprint versus storing
 // (base_line, num_bits, symbol) -- shared memory per block is what bounds how many sequence
 // streams an SM can decode at once.
 // Symbols are clamped to 63: every code above 35 (LL), 52 (ML) or 31 (OF) is an error downstream.
@@ -27,7 +27,7 @@ __device__ __forceinline__ uint32_t fse_entry_sym(uint32_t e) { return e >> 10; 
 __device__ __forceinline__ uint32_t fse_entry_nbits(uint32_t e, uint32_t log) { return log - (31u - (uint32_t)__clz(e & 1023u)); }
 __device__ __forceinline__ uint32_t fse_entry_base(uint32_t e, uint32_t nb, uint32_t log) { return ((e & 1023u) << nb) - (1u << log); }
 
-// Serial (one lane).  probs[] receives up to FSE_MAX_SYMBOLS entries; n_probs counts all of them.
+// Serial (one lane).  probs[] receives up to FSE_MAX_SYMBOLS entries (nullptr: only measure the description); n_probs counts all of them.
 // A description whose accuracy log passes max_log (the reference's check) but exceeds FSE_MAX_LOG -- only possible
 // for Huffman weights, where the reference passes 100 (huff0_decoder.cairo:176) -- is still parsed to the end so
 // that every error the reference would raise is raised; if it parses cleanly CZS_UNSUPPORTED is returned with
@@ -59,7 +59,7 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
         else if (unchecked > mask) value = unchecked - low_threshold;
         else value = unchecked;
         const int prob = (int)value - 1;
-        if (n_probs < FSE_MAX_SYMBOLS) { if (!oversize) probs[n_probs] = (int16_t)prob; else if (probs32) probs32[n_probs] = prob; }
+        if (n_probs < FSE_MAX_SYMBOLS) { if (!oversize) { if (probs) probs[n_probs] = (int16_t)prob; } else if (probs32) probs32[n_probs] = prob; }
         n_probs++;
         if (prob != 0) {
             counter += prob > 0 ? (uint32_t)prob : 1u;
@@ -68,7 +68,7 @@ __device__ inline int32_t fse_read_probabilities(const uint8_t* p, int len, int 
                 uint32_t skip;
                 if (!br.get(2, skip)) return CZS_FSE_GET_BITS_ERROR;
                 for (uint32_t k = 0; k < skip; k++) {
-                    if (n_probs < FSE_MAX_SYMBOLS) { if (!oversize) probs[n_probs] = 0; else if (probs32) probs32[n_probs] = 0; }
+                    if (n_probs < FSE_MAX_SYMBOLS) { if (!oversize) { if (probs) probs[n_probs] = 0; } else if (probs32) probs32[n_probs] = 0; }
                     n_probs++;
                 }
                 if (skip != 3) break;
