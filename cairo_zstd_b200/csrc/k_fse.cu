@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
     }
     if (sl.blk == NONE32) return;
 #else
-    if (warp != 0) return;
+    if (warp != 0) return;  // (rotating the decode warp over the CTAs of an SM was measured: 28.3 -> 33.4 ms; the hardware already spreads them over the schedulers)
 
     // ---- phase 2: lane = block ----
     if (lane >= FSE_SLOTS) return;
@@ -664,22 +664,29 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             br.chunk -= left ? 1 : 0;
         };
         uint32_t lle, mle, nbLL, nbML, nbOF;
+        uint32_t llc = (uint32_t)__cvta_generic_to_shared(sm.ll_code), mlc = (uint32_t)__cvta_generic_to_shared(sm.ml_code);
+        asm volatile("" : "+r"(llc), "+r"(mlc));  // opaque, as above: one shift and one scaled add per code lookup
+        const uint32_t kLL = logLL - 9u, kOF = logOF - 9u, kML = logML - 9u;
         auto prep = [&]() {  // what the next step needs from the entries just looked up
-            lle = sm.ll_code[fse_entry_sym(eLL)]; mle = sm.ml_code[fse_entry_sym(eML)];
-            nbLL = fse_entry_nbits(eLL, logLL); nbML = fse_entry_nbits(eML, logML); nbOF = fse_entry_nbits(eOF, logOF);
+            lle = lds32(llc + (fse_entry_sym(eLL) << 2)); mle = lds32(mlc + (fse_entry_sym(eML) << 2));
+            // num_bits = log - floor(log2(next_state)), next_state in the entry's low 10 bits (the shift can go to the other pipe)
+            nbLL = kLL + (uint32_t)__clz(eLL << 22); nbML = kML + (uint32_t)__clz(eML << 22); nbOF = kOF + (uint32_t)__clz(eOF << 22);
         };
         load_window(); prep();
         // One sequence (:223-286).  MORE = false is the last sequence: states are not updated (:258).
+        uint32_t trouble_of = 0;  // OR of the offset entries: bit 15 set <=> an offset code >= 32 turned up
         auto step = [&](auto more_tag) -> Seq {
             constexpr bool MORE = decltype(more_tag)::value;
-            const uint32_t ofc = fse_entry_sym(eOF);
-            trouble |= (ofc << 15) | lle | mle;  // ofc >= 32 puts its bit 5 at bit 20
-            const uint32_t llb = lle >> 27, mlb = mle >> 27, ofb = ofc & 31u;
+            trouble |= lle | mle;
+            trouble_of |= eOF;
+            const uint32_t llb = lle >> 27, mlb = mle >> 27, ofb = fse_entry_sym(eOF) & 31u;
             const uint32_t extras = ofb + mlb + llb;  // read in the order OF, ML, LL (:239)
-            const uint32_t ofv = shr_clamp(x2, 32u - ofb);
+            // funnel shifts: (hi << n) | (lo >> (32 - n)) is "hi, then the top n bits of lo" -- also right for n = 0
+            const uint32_t v = __funnelshift_l(x2, 1u, ofb);  // (1 << ofb) + the ofb extra bits (:243)
             const uint32_t y = __funnelshift_l(x1, x2, ofb);
-            const uint32_t mlv = shr_clamp(y, 32u - mlb), llv = shr_clamp(y << mlb, 32u - llb);
-            const uint32_t ll = (lle & 0xFFFFFu) + llv, ml = (mle & 0xFFFFFu) + mlv;
+            const uint32_t mlv = __funnelshift_l(y, 0u, mlb), llv = __funnelshift_l(y << mlb, 0u, llb);
+            // literal-length baselines are multiples of 2^bits (16,18,20,22 | 24,28 | 32,40 | 48 | 64 ...): "|" is "+"; match-length ones are not (35,37,..)
+            const uint32_t ll = (lle & 0xFFFFFu) | llv, ml = (mle & 0xFFFFFu) + mlv;
             if (MORE) {
                 // state bits (LL, ML, OF, :258-276) start `extras` bits into the window
                 const uint32_t za = __funnelshift_l(x1, x2, extras), zb = __funnelshift_l(x0, x1, extras);  // shift taken modulo 32
@@ -696,7 +703,6 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             } else {
                 br.P -= (int)extras;
             }
-            const uint32_t v = (1u << ofb) + ofv;  // :243
             // do_offset_history (sequence_execution.cairo:85-129) with selects only:
             // idx 0,1,2 = history slot, 3 = h0 - 1 (reachable only when ll == 0)
             const uint32_t idx = v - (ll != 0);
@@ -712,7 +718,11 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             h0 = act;
             ml_total += ml;  // the block's output size is regen + sum(ml): what czb_frame_sizes_* reports without executing
             if (MORE) prep();
-            return (Seq)ll | ((Seq)ml << 17) | ((Seq)off29_pack(act) << 35);
+            // off29_pack without its branches: symbolic v = SYM_BASE + (k << 24) + SYM_MID - c  ->  1 << 28 | k << 24 | c
+            //   = v - 2 * (v & 0xFFFFFF) + (1 << 28) + 2 * SYM_MID - SYM_BASE - SYM_MID   (mod 2^32; c < SYM_MID)
+            const uint32_t packed_sym = act - 2u * (act & 0x00FFFFFFu) + ((1u << 28) + SYM_MID - SYM_BASE);
+            const uint32_t packed = act >= SYM_BASE ? packed_sym : min(act, OFF29_CLAMP);
+            return (Seq)ll | ((Seq)ml << 17) | ((Seq)packed << 35);
         };
         int p1 = 0x40000000, p2 = 0x40000000, p3 = 0x40000000;  // P at the start of the previous three groups of four ("far above": nothing may stay in flight yet)
         uint32_t i = 0;
@@ -746,7 +756,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
         }
         cp_async_wait<0>();
         // rem only ever decreases: one look tells whether it went negative on the way (:281-283)
-        if ((trouble & FSE_BAD_CODE) || br.rem() < 0) return CZS_NOT_DECODED;  // placeholder: the exact form decides
+        if (((trouble & FSE_BAD_CODE) | (trouble_of & (32u << 10))) || br.rem() < 0) return CZS_NOT_DECODED;  // placeholder: the exact form decides
         return br.rem() > 0 ? CZS_SEQ_EXTRA_BITS : CZS_OK;  // :292-296
     };
 #endif
