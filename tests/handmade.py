@@ -99,3 +99,68 @@ def frame_with_weight_table(log, probs, weight_stream: bytes, huf_stream: bytes,
     else:
         fhd = bytes([0x60]) + struct.pack("<H", regen - 256)
     return MAGIC + fhd + bh + block
+
+
+def greedy_sequences_frame(n_seq, seed, history_blocks=1, max_of_code=24, window_log=24):
+    """A frame whose sequence section consumes as many bits per sequence as valid input can: `history_blocks` raw blocks of
+    128 KiB (so that large offsets are legal), then ONE compressed block with raw literals and `n_seq` sequences whose three FSE
+    tables are built so that every state update reads the table's full accuracy log (9 + 9 + 8 bits): the symbols in use are
+    "less than one" symbols (one cell each at the top of the table, baseline 0, num_bits = log:
+    src/fse/fse_decoder.cairo:169-189, :377-400), so the encoder is free to name any next state.  Offset codes grow with the
+    output (up to `max_of_code` extra bits); literal lengths use code 22 (3 extra bits), match lengths code 32 (1 extra bit).
+    ~50 bits per sequence against ~25 for text: several 16-byte chunks of the backward bitstream per four sequences, which is what
+    the ring look-after of k_fse has to keep up with.  Returns (frame, expected output)."""
+    import random
+    rng = random.Random(seed)
+    out = bytearray()
+    body = b""
+    for _ in range(history_blocks):
+        raw = bytes(rng.getrandbits(8) for _ in range(1 << 17))
+        body += (0 | (0 << 1) | ((1 << 17) << 3)).to_bytes(3, "little") + raw
+        out += raw
+    # tables: symbol 0 takes every cell the used symbols leave
+    LL_LOG, OF_LOG, ML_LOG = 9, 8, 9
+    ll_probs = [511] + [0] * 21 + [-1]                      # code 22: baseline 32, 3 bits
+    ml_probs = [511] + [0] * 31 + [-1]                      # code 32: baseline 35, 1 bit
+    of_codes = list(range(2, max_of_code + 1))             # offset value (1 << N) + extra >= 4: never a repeat code
+    of_probs = [256 - len(of_codes), 0] + [-1] * len(of_codes)
+    ll_state = (1 << LL_LOG) - 1                            # the only "less than one" symbol sits in the top cell
+    ml_state = (1 << ML_LOG) - 1
+    of_state = {c: (1 << OF_LOG) - 1 - k for k, c in enumerate(of_codes)}  # top cells in symbol order
+    bits = []
+    def put(v, n):
+        bits.extend((v >> (n - 1 - k)) & 1 for k in range(n))
+    lits = bytearray()
+    seqs = []
+    produced = len(out)
+    for _ in range(n_seq):
+        ll = 32 + rng.randrange(8)
+        ml = 35 + rng.randrange(2)
+        before = produced + ll
+        n = min(max_of_code, (before + 3).bit_length() - 1)
+        if rng.random() < 0.1:
+            n = rng.randrange(2, n + 1)
+        extra = rng.randrange(0, min((1 << n) - 1, before + 3 - (1 << n)) + 1)
+        seqs.append((ll, ml, n, extra))
+        produced = before + ml
+    put(ll_state, LL_LOG); put(of_state[seqs[0][2]], OF_LOG); put(ml_state, ML_LOG)   # initial states: LL, OF, ML
+    for i, (ll, ml, n, extra) in enumerate(seqs):
+        put(extra, n); put(ml - 35, 1); put(ll - 32, 3)        # extra bits: offset, match length, literal length
+        if i + 1 < len(seqs):
+            put(ll_state, LL_LOG); put(ml_state, ML_LOG); put(of_state[seqs[i + 1][2]], OF_LOG)  # state updates: LL, ML, OF
+        new = bytes(rng.getrandbits(8) for _ in range(ll))
+        lits += new
+        out += new
+        off = (1 << n) + extra - 3
+        assert 0 < off <= len(out)
+        for _ in range(ml):
+            out.append(out[-off])
+    assert len(lits) < (1 << 20)
+    lit_hdr = (0 | (3 << 2) | (len(lits) << 4)).to_bytes(3, "little")
+    assert 128 <= n_seq < 0x7F00
+    seq_hdr = bytes([(n_seq >> 8) + 128, n_seq & 255, (2 << 6) | (2 << 4) | (2 << 2)])
+    block = (lit_hdr + bytes(lits) + seq_hdr + fse_normalized_counts(LL_LOG, ll_probs) + fse_normalized_counts(OF_LOG, of_probs)
+             + fse_normalized_counts(ML_LOG, ml_probs) + rev_stream(bits))
+    body += (1 | (2 << 1) | (len(block) << 3)).to_bytes(3, "little") + block
+    fhd = bytes([0x80, (window_log - 10) << 3]) + struct.pack("<I", len(out))   # 4-byte frame content size, window descriptor, no checksum
+    return MAGIC + fhd + body, bytes(out)

@@ -13,7 +13,7 @@ import pytest
 import oracle_lib as O
 import cairo_zstd_b200 as czb
 from cairo_zstd_b200 import workloads as W
-from gpu_common import gpu_decode
+from gpu_common import compare_with_oracle, gpu_decode
 
 pytestmark = pytest.mark.gpu
 
@@ -93,3 +93,21 @@ def test_huffman_weight_tables_with_accuracy_log_above_9(corpus):
             assert outs[i] == want
         past_table += st not in FSE_DESC_ERRORS
     assert past_table >= len(frames) // 2, past_table
+
+
+def test_sequence_sections_that_read_fifty_bits_per_sequence():
+    """k_fse's ring look-after under the heaviest valid bit consumption (tests/handmade.greedy_sequences_frame: every state update
+    reads the full accuracy log, offset codes carry up to 24 extra bits): several 16-byte chunks of the backward bitstream go by
+    per four sequences, so the extra refills, the mirror of the ring's top chunk and the adaptive cp.async wait depth all run,
+    with blocks of different lengths side by side in one CTA (tails of one to four sequences included).  Bit-exact against the
+    oracle, whose output was pinned against libzstd on the same construction (tests/test_oracle.py)."""
+    import handmade as H
+    frames, wants = [], []
+    for k, (n_seq, hist) in enumerate([(129, 1), (130, 1), (131, 1), (132, 1), (133, 2), (400, 1), (1500, 8), (3000, 40), (2500, 136)]
+                                      + [(200 + 37 * j, 1 + j % 3) for j in range(40)]):
+        f, w = H.greedy_sequences_frame(n_seq, 100 + k, history_blocks=hist)
+        frames.append(f); wants.append(w)
+    caps = [len(w) for w in wants]
+    outs, res = compare_with_oracle(frames, caps, label="greedy")
+    for o, w, r in zip(outs, wants, res):
+        assert r.status == 0 and o == w

@@ -309,3 +309,15 @@ def test_handmade_huffman_split_frames_decode():
     f, _ = H.huf4_two_symbol_frame([[0, 1], [1, 1], [0, 0], [1, 0]])
     b = bytearray(f); b[9] += 0x10  # literals header says 9 regenerated bytes, the streams hold 8
     assert O.decode_frame(bytes(b), dst_cap=64)[0] == {v: k for k, v in api.STATUS_NAMES.items()}["CZS_DECODED_LITERAL_COUNT_MISMATCH"]
+
+
+def test_greedy_sequence_frames_are_valid_zstd_and_pin_the_oracle():
+    """tests/handmade.greedy_sequences_frame: hand-assembled sequence sections that read the full accuracy log on every state
+    update and offset codes of up to 20 extra bits (~50 bits per sequence).  The expected output comes from the construction
+    itself; the oracle and libzstd (an independent decoder) must both reproduce it."""
+    import handmade as H
+    for n_seq, seed, hist in ((130, 1, 1), (131, 2, 1), (133, 3, 2), (900, 4, 8)):
+        frame, want = H.greedy_sequences_frame(n_seq, seed, history_blocks=hist)
+        st, out, res = O.decode_frame(frame, dst_cap=len(want))
+        assert st == 0 and out == want and res.content_size == len(want), (n_seq, st)
+        assert W.libzstd_decompress(frame, len(want)) == want
