@@ -93,7 +93,37 @@ __device__ __forceinline__ Vec16 load16_unaligned(const uint8_t* __restrict__ sr
 }
 // t[0..n) = the first n bytes of x (byte stores into the shared-memory tile).  Groups of four bytes are skipped
 // warp-uniformly when no lane needs them, so short segments do not pay for sixteen predicated stores.
+// The stores go through inline asm on ONE address register with immediate offsets: left to itself ptxas re-forms
+// "tile base + alignment + segment start" under every store's predicate (a three-input add per byte, to save a register under the
+// 72-register cap): 4 instructions per byte instead of 3 on the integer pipe that issues one instruction per two cycles.
+// No "memory" clobber on the stores (the loads of the next vector may move across them); tile_stores_done() orders them
+// before anything that reads the tile.
+#ifndef CZB_EXEC_ASM_ST
+#define CZB_EXEC_ASM_ST 1
+#endif
+__device__ __forceinline__ uint32_t tile_addr(const uint8_t* t) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(t);
+    asm volatile("" : "+r"(a));  // opaque: one register, not a sum to re-form
+    return a;
+}
+// byte K of the segment, if the segment has one: the predicate lives inside the asm (an `if` around it becomes a divergent branch per byte)
+template <int K>
+__device__ __forceinline__ void sts_u8_if(uint32_t a, uint32_t v, uint32_t n) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %3, %2;\n\t@p st.shared.u8 [%0+%2], %1;\n\t}" ::"r"(a), "r"(v), "n"(K), "r"(n));
+}
+__device__ __forceinline__ void tile_stores_done() { asm volatile("" ::: "memory"); }
+template <int G>
+__device__ __forceinline__ void store4_to_tile(uint32_t a, uint32_t w, uint32_t n) {
+    sts_u8_if<4 * G>(a, w, n); sts_u8_if<4 * G + 1>(a, w >> 8, n); sts_u8_if<4 * G + 2>(a, w >> 16, n); sts_u8_if<4 * G + 3>(a, w >> 24, n);
+}
 __device__ __forceinline__ void store16_to_tile(uint8_t* t, const Vec16& x, uint32_t n) {
+#if CZB_EXEC_ASM_ST
+    const uint32_t a = tile_addr(t);
+    store4_to_tile<0>(a, x.v[0], n);
+    if (__any_sync(0xFFFFFFFFu, n > 4u)) store4_to_tile<1>(a, x.v[1], n);
+    if (__any_sync(0xFFFFFFFFu, n > 8u)) store4_to_tile<2>(a, x.v[2], n);
+    if (__any_sync(0xFFFFFFFFu, n > 12u)) store4_to_tile<3>(a, x.v[3], n);
+#else
 #pragma unroll
     for (int g = 0; g < 4; g++) {
         if (g == 0 || __any_sync(0xFFFFFFFFu, n > 4u * g)) {
@@ -101,6 +131,7 @@ __device__ __forceinline__ void store16_to_tile(uint8_t* t, const Vec16& x, uint
             for (int k = 4 * g; k < 4 * g + 4; k++) if ((uint32_t)k < n) t[k] = (uint8_t)(x.v[g] >> (8 * (k & 3)));
         }
     }
+#endif
 }
 
 // All lanes copy n bytes src -> tile + dst_off for the lane `j` that owns the job (arguments are taken from lane j).
@@ -114,8 +145,13 @@ __device__ __forceinline__ void coop_copy_to_tile(uint8_t* tile, unsigned lane, 
 
 // the same without the votes
 __device__ __forceinline__ void store16_to_tile_all(uint8_t* t, const Vec16& x, uint32_t n) {
+#if CZB_EXEC_ASM_ST
+    const uint32_t a = tile_addr(t);
+    store4_to_tile<0>(a, x.v[0], n); store4_to_tile<1>(a, x.v[1], n); store4_to_tile<2>(a, x.v[2], n); store4_to_tile<3>(a, x.v[3], n);
+#else
 #pragma unroll
     for (int k = 0; k < 16; k++) if ((uint32_t)k < n) t[k] = (uint8_t)(x.v[k >> 2] >> (8 * (k & 3)));
+#endif
 }
 
 // Sequence-centric execution of one chunk whose output span fits the tile: lane = sequence.  The first 16 bytes of
@@ -161,6 +197,7 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
         const Vec16 xl = load16_unaligned(lits + my_lit, nl), xm = load16_unaligned<CG_LOADS>(msrc, nm);
         store16_to_tile(tile + segA, xl, nl);      // literal runs average under three bytes: later groups are usually skipped
         store16_to_tile_all(tile + segM, xm, nm);  // matches average nine: some lane always needs every group, votes only cost
+        tile_stores_done();
     }
     // Tails beyond the first 16 bytes are rare (a few per cent of the segments) and may be long: the whole warp
     // copies each one instead of every lane looping in lockstep for the longest.
@@ -179,6 +216,7 @@ __device__ __forceinline__ void exec_chunk_tile(uint8_t* tile_base, uint8_t* oba
         const uint32_t nm = late ? (ml < 16u ? ml : 16u) : 0u;
         if (__any_sync(0xFFFFFFFFu, late)) {
             store16_to_tile(tile + segM, load16_unaligned<true>(msrc, nm), nm);
+            tile_stores_done();
             for (unsigned m = __ballot_sync(0xFFFFFFFFu, late && ml > 16u); m; m &= m - 1)
                 coop_copy_to_tile<true>(tile, lane, __ffs(m) - 1, segM + 16u, msrc + 16, ml - 16u);
             __syncwarp();
