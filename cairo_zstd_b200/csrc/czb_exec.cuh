@@ -75,17 +75,36 @@ __device__ __forceinline__ void warp_fill(uint8_t* dst, uint8_t byte, uint32_t n
     for (uint32_t i = lane; i < n; i += 32) dst[i] = byte;
 }
 
-// 16 source bytes starting at src (any alignment, global or shared memory) as four little-endian words.  Only the
+// 16 source bytes starting at src (any alignment, GLOBAL memory) as four little-endian words.  Only the
 // aligned 32-bit words that hold one of the first n bytes are read.
+// As plain C ptxas turns the "needed?" chain into branches around the loads, which skip a word altogether when no lane needs it
+// (literal runs average three bytes: words 2..4 are almost never read).  -DCZB_EXEC_ASM_LD=1 makes every word one compare and one
+// predicated ld.global instead (no BSSY / BRA / BSYNC): measured SLOWER (k_exec 43.2 -> 44.4 ms per three waves), five always-issued
+// loads cost more than the branches.
 struct Vec16 { uint32_t v[4]; };
+#ifndef CZB_EXEC_ASM_LD
+#define CZB_EXEC_ASM_LD 0
+#endif
+template <bool CG, int K, int THR>  // word K of the vector's aligned source words, read iff x > THR
+__device__ __forceinline__ uint32_t ldg32_if_gt(const uint32_t* w, uint32_t x) {
+    uint32_t v;
+    if (CG) asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %2, %4;\n\tmov.u32 %0, 0;\n\t@p ld.global.cg.u32 %0, [%1+%3];\n\t}" : "=r"(v) : "l"(w), "r"(x), "n"(4 * K), "n"(THR) : "memory");
+    else asm volatile("{\n\t.reg .pred p;\n\tsetp.gt.u32 p, %2, %4;\n\tmov.u32 %0, 0;\n\t@p ld.global.ca.u32 %0, [%1+%3];\n\t}" : "=r"(v) : "l"(w), "r"(x), "n"(4 * K), "n"(THR) : "memory");
+    return v;
+}
 template <bool CG = false>  // CG: read through L2 (data another warp of the CTA has just written)
 __device__ __forceinline__ Vec16 load16_unaligned(const uint8_t* __restrict__ src, uint32_t n) {
     const uintptr_t a = reinterpret_cast<uintptr_t>(src);
     const uint32_t mis = (uint32_t)(a & 3), sh = mis * 8, need = n + mis;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+#if CZB_EXEC_ASM_LD
+    const uint32_t w0 = ldg32_if_gt<CG, 0, 0>(w, n);
+    const uint32_t w1 = ldg32_if_gt<CG, 1, 4>(w, need), w2 = ldg32_if_gt<CG, 2, 8>(w, need), w3 = ldg32_if_gt<CG, 3, 12>(w, need), w4 = ldg32_if_gt<CG, 4, 16>(w, need);
+#else
     auto ld = [&](int k) -> uint32_t { return CG ? __ldcg(w + k) : w[k]; };
     const uint32_t w0 = n ? ld(0) : 0u;
     const uint32_t w1 = need > 4 ? ld(1) : 0u, w2 = need > 8 ? ld(2) : 0u, w3 = need > 12 ? ld(3) : 0u, w4 = need > 16 ? ld(4) : 0u;
+#endif
     Vec16 r;
     r.v[0] = __funnelshift_r(w0, w1, sh); r.v[1] = __funnelshift_r(w1, w2, sh);
     r.v[2] = __funnelshift_r(w2, w3, sh); r.v[3] = __funnelshift_r(w3, w4, sh);

@@ -193,6 +193,8 @@ __global__ void __launch_bounds__(EXEC_WARPS * 32, EXEC_MIN_CTAS) k_exec(const c
     const czb_frame_desc fd = descs[f];
     const uint8_t* src = fd.src;
     uint8_t* dst = fd.dst;
+    // (telling the compiler that src / dst are global memory -- __builtin_assume(__isGlobal(..)): LDG / STG instead of generic LD / ST --
+    // was measured: k_exec 43.2 -> 44.9 ms per three waves)
     const uint64_t cap = fd.dst_cap < MAX_FRAME_OUT ? fd.dst_cap : MAX_FRAME_OUT;
     const int32_t cap_status = fd.dst_cap < MAX_FRAME_OUT ? CZS_DST_TOO_SMALL : CZS_UNSUPPORTED;
 
