@@ -320,7 +320,8 @@ def run_b200(args, rank, world, local_rank):
                                            "note": "fraction of the SMs' issue slots the dominant kernel uses; the kernel is latency / issue bound, not HBM bound"}
             wp = sum(k["warp_inst_per_frame"] for kn, k in tj["kernels"].items())
             roofline["whole_path"]["issue_slot_frac"] = wp * n / (ms_per_step * 1e-3 * sms * 4 * clk)
-            roofline["whole_path"]["dram_traffic_over_algorithmic"] = tj.get("whole_path_traffic_over_algorithmic")
+            # DRAM bytes of all decode kernels per frame (same capture) over the algorithmic C + D per frame of THIS run
+            roofline["whole_path"]["dram_traffic_over_algorithmic"] = sum(k["bytes_per_frame"] for k in tj["kernels"].values()) / (alg_bytes_step / n)
         except Exception as e:
             sys.stderr.write(f"traffic/issue-slot annotation skipped: {e}\n")
 
