@@ -79,6 +79,18 @@ struct WinView {
     }
     __device__ __forceinline__ void store16(int x, const Vec16& v, uint32_t n) const {
         const uint32_t a = gb + (uint32_t)x;
+#if CZB_EXEC_ASM_ST
+        // no lane's sixteen bytes wrap around the window's end: one address per lane and immediate offsets (see store16_to_tile)
+        if (__all_sync(0xFFFFFFFFu, (a & BIG_WIN_MASK) <= BIG_WIN - 16u)) {
+            const uint32_t sa = tile_addr(win) + (a & BIG_WIN_MASK);
+            store4_to_tile<0>(sa, v.v[0], n);
+            if (__any_sync(0xFFFFFFFFu, n > 4u)) store4_to_tile<1>(sa, v.v[1], n);
+            if (__any_sync(0xFFFFFFFFu, n > 8u)) store4_to_tile<2>(sa, v.v[2], n);
+            if (__any_sync(0xFFFFFFFFu, n > 12u)) store4_to_tile<3>(sa, v.v[3], n);
+            tile_stores_done();
+            return;
+        }
+#endif
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             if (g == 0 || __any_sync(0xFFFFFFFFu, n > 4u * g)) {

@@ -140,6 +140,19 @@ struct FlowWin {
         return r;
     }
     __device__ __forceinline__ void store16(uint32_t p, const Vec16& v, uint32_t n) const {
+#if CZB_EXEC_ASM_ST
+        // No lane's sixteen bytes wrap around the window's end (all but one vector in FLOW_WIN / 16): one address per lane, immediate offsets,
+        // the byte predicates inside the asm (czb_exec.cuh) instead of an add, a mask and an add per byte.
+        if (__all_sync(0xFFFFFFFFu, (p & FLOW_WIN_MASK) <= FLOW_WIN - 16u)) {
+            const uint32_t a = tile_addr(win) + (p & FLOW_WIN_MASK);
+            store4_to_tile<0>(a, v.v[0], n);
+            if (__any_sync(0xFFFFFFFFu, n > 4u)) store4_to_tile<1>(a, v.v[1], n);
+            if (__any_sync(0xFFFFFFFFu, n > 8u)) store4_to_tile<2>(a, v.v[2], n);
+            if (__any_sync(0xFFFFFFFFu, n > 12u)) store4_to_tile<3>(a, v.v[3], n);
+            tile_stores_done();
+            return;
+        }
+#endif
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             if (g == 0 || __any_sync(0xFFFFFFFFu, n > 4u * g)) {
