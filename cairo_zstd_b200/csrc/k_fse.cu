@@ -47,6 +47,7 @@ struct FseSlot {
     int8_t log[3];         // accuracy log; 0 = RLE (one entry); -1 = never initialised
     uint8_t first_in_frame;
     uint8_t any_rle;
+    uint8_t risky;         // some table holds a symbol beyond the code tables (LL > 35, OF > 31, ML > 52): the lean loop, which does not look, is skipped
 };
 
 struct alignas(16) FseWarpTmp {
@@ -58,7 +59,7 @@ static_assert(sizeof(FseWarpTmp) * FSE_WARPS >= FSE_SLOTS * (RevBitsWin::RING + 
 #ifndef CZB_FSE_SPLIT
 #define CZB_FSE_SPLIT 0  // 0: one warp, lean step (default); 1: the step split over two warps (state machine | values, history, records: measured no faster); 2: one warp, round-1 step
 #endif
-constexpr int FSE_HAND_STEPS = 4;  // steps per hand-over buffer: one barrier pair and three 16-byte vectors per lane
+[[maybe_unused]] constexpr int FSE_HAND_STEPS = 4;  // steps per hand-over buffer: one barrier pair and three 16-byte vectors per lane
 struct FseSmem {
     uint16_t entries[FSE_SLOTS * FSE_SLOT_ENTRIES + 64 + 32 + 64];  // per-slot tables, then predefined LL, OF, ML
     union {
@@ -139,8 +140,11 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 uint32_t cursor = d.seq_src_off;
                 const uint32_t end = d.seq_src_off + d.seq_src_len;
                 int32_t st = CZS_OK;
-                bool any_rle = false;
+                bool any_rle = false, risky = false;
                 for (int k = 0; k < 3 && st == CZS_OK; k++) {
+                    // lookup_ll_code / offset codes / lookup_ml_code (:235-237, :299-395); offset code 31 is legal but its value can pass
+                    // REAL_OFF_CLAMP, which the lean loop does not apply: it goes to the exact loop as well
+                    const uint32_t n_codes = k == 0 ? 36u : (k == 1 ? 31u : 53u);
                     const int region = s * FSE_SLOT_ENTRIES + (k == 0 ? FSE_LL_OFS : (k == 1 ? FSE_OF_OFS : FSE_ML_OFS));
                     uint32_t mode = ((uint32_t)d.modes >> (6 - 2 * k)) & 3u;
                     const uint8_t* p = fsrc + cursor;
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                         } else {
                             sm.entries[region] = fse_entry(p[0], 1u); sl.log[k] = 0;
                             any_rle = true;
+                            risky = risky || p[0] >= n_codes;
                             if (own) cursor += 1;
                         }
                     } else {  // MODE_FSE
@@ -180,6 +185,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                         if (pst != CZS_OK) { if (own) st = pst; }
                         else {
                             sl.n_probs[k] = (uint16_t)n_probs; sl.log[k] = (int8_t)log;
+                            risky = risky || (uint32_t)n_probs > n_codes;  // the last symbol of a description never has probability zero
                             if (own) cursor += (uint32_t)used;
                         }
                     }
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
                 sl.blk = bi; sl.n_seq = d.n_seq; sl.status = st;
                 sl.bits = fsrc + cursor; sl.bits_len = end - cursor;
                 sl.out = seq_scratch + d.seq_off;
-                sl.first_in_frame = d.first_in_frame; sl.any_rle = any_rle ? 1 : 0;
+                sl.first_in_frame = d.first_in_frame; sl.any_rle = any_rle ? 1 : 0; sl.risky = risky ? 1 : 0;
             }
         }
     }
@@ -622,7 +628,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
         constexpr uint32_t RING_STRIDE = RevBitsWin::RING + 16;
         RevBitsWin br;
         if (!br.init(sl.bits, (int)sl.bits_len, (uint32_t)__cvta_generic_to_shared(sm.tmp) + lane * RING_STRIDE + 16u)) return CZS_NOT_DECODED;
-        if (sl.log[0] < 0 || sl.log[1] < 0 || sl.log[2] < 0) return CZS_NOT_DECODED;
+        if (sl.log[0] < 0 || sl.log[1] < 0 || sl.log[2] < 0 || sl.risky) return CZS_NOT_DECODED;  // risky: a code beyond the tables may turn up (:235-237), and this loop does not look
         const uint32_t dummy = (uint32_t)__cvta_generic_to_shared(sm.tmp) + FSE_SLOTS * RING_STRIDE;
         const uint32_t logLL = (uint32_t)sl.log[0], logOF = (uint32_t)sl.log[1], logML = (uint32_t)sl.log[2];
         const uint32_t mLL = (1u << logLL) - 1u, mOF = (1u << logOF) - 1u, mML = (1u << logML) - 1u;
@@ -642,7 +648,6 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
         }
         const uint32_t n = sl.n_seq;
         Seq* out = sl.out;
-        uint32_t trouble = 0;  // bit 20 set <=> a code beyond the tables turned up (:235-237)
         uint32_t x0, x1, x2;   // 96 unread bits at P, x2 first: extra bits (<= 63) and state bits (<= 26) of one step all lie inside
         auto load_window = [&]() {
             const uint32_t a = br.ring + (((uint32_t)br.P >> 3) & (RevBitsWin::RING - 4)), sh = (uint32_t)br.P & 31u;
@@ -674,11 +679,8 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
         };
         load_window(); prep();
         // One sequence (:223-286).  MORE = false is the last sequence: states are not updated (:258).
-        uint32_t trouble_of = 0;  // OR of the offset entries: bit 15 set <=> an offset code >= 32 turned up
-        auto step = [&](auto more_tag) -> Seq {
+        auto step = [&](auto more_tag, auto sym_tag) -> Seq {  // sym_tag: some lane of the warp runs on symbolic history (a block that is not first in its frame)
             constexpr bool MORE = decltype(more_tag)::value;
-            trouble |= lle | mle;
-            trouble_of |= eOF;
             const uint32_t llb = lle >> 27, mlb = mle >> 27, ofb = fse_entry_sym(eOF) & 31u;
             const uint32_t extras = ofb + mlb + llb;  // read in the order OF, ML, LL (:239)
             // funnel shifts: (hi << n) | (lo >> (32 - n)) is "hi, then the top n bits of lo" -- also right for n = 0
@@ -711,19 +713,23 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             cand = idx == 2 ? h2 : cand;
             cand = idx == 1 ? h1 : cand;
             cand = idx == 0 ? h0 : cand;
-            const uint32_t nz = min(v - 3u, REAL_OFF_CLAMP);
+            const uint32_t nz = v - 3u;  // < 2^31: offset code 31 never gets here (risky), so no REAL_OFF_CLAMP
             const uint32_t act = rep ? cand : nz;
             h2 = (rep & (idx <= 1)) ? h2 : h1;
             h1 = (rep & (idx == 0)) ? h1 : h0;
             h0 = act;
             ml_total += ml;  // the block's output size is regen + sum(ml): what czb_frame_sizes_* reports without executing
             if (MORE) prep();
-            // off29_pack without its branches: symbolic v = SYM_BASE + (k << 24) + SYM_MID - c  ->  1 << 28 | k << 24 | c
-            //   = v - 2 * (v & 0xFFFFFF) + (1 << 28) + 2 * SYM_MID - SYM_BASE - SYM_MID   (mod 2^32; c < SYM_MID)
-            const uint32_t packed_sym = act - 2u * (act & 0x00FFFFFFu) + ((1u << 28) + SYM_MID - SYM_BASE);
-            const uint32_t packed = act >= SYM_BASE ? packed_sym : min(act, OFF29_CLAMP);
+            uint32_t packed = min(act, OFF29_CLAMP);
+            if (decltype(sym_tag)::value) {
+                // off29_pack without its branches: symbolic v = SYM_BASE + (k << 24) + SYM_MID - c  ->  1 << 28 | k << 24 | c
+                //   = v - 2 * (v & 0xFFFFFF) + (1 << 28) + 2 * SYM_MID - SYM_BASE - SYM_MID   (mod 2^32; c < SYM_MID)
+                const uint32_t packed_sym = act - 2u * (act & 0x00FFFFFFu) + ((1u << 28) + SYM_MID - SYM_BASE);
+                packed = act >= SYM_BASE ? packed_sym : packed;
+            }
             return (Seq)ll | ((Seq)ml << 17) | ((Seq)packed << 35);
         };
+        auto run = [&](auto sym_tag) {
         int p1 = 0x40000000, p2 = 0x40000000, p3 = 0x40000000;  // P at the start of the previous three groups of four ("far above": nothing may stay in flight yet)
         uint32_t i = 0;
         for (; i + 4 < n; i += 4) {
@@ -738,7 +744,7 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
             else cp_async_wait<1>();
             p3 = p2; p2 = p1; p1 = br.P;
             // four records leave as two 16-byte stores: a block's slice of the scratch is 32-byte aligned (k_fill_blocks)
-            const Seq r0 = step(std::true_type{}), r1 = step(std::true_type{}), r2 = step(std::true_type{}), r3 = step(std::true_type{});
+            const Seq r0 = step(std::true_type{}, sym_tag), r1 = step(std::true_type{}, sym_tag), r2 = step(std::true_type{}, sym_tag), r3 = step(std::true_type{}, sym_tag);
             uint4* o4 = reinterpret_cast<uint4*>(out + i);
             __stcs(o4, make_uint4((uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32)));
             __stcs(o4 + 1, make_uint4((uint32_t)r2, (uint32_t)(r2 >> 32), (uint32_t)r3, (uint32_t)(r3 >> 32)));
@@ -749,14 +755,16 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
         }
         for (; i < n; i++) {  // the block's last one to four sequences
             cp_async_wait<0>();
-            const Seq r = i + 1 < n ? step(std::true_type{}) : step(std::false_type{});
+            const Seq r = i + 1 < n ? step(std::true_type{}, sym_tag) : step(std::false_type{}, sym_tag);
             __stcs(out + i, r);  // written once, read by a later kernel: streaming store
             refill(__activemask());
             cp_async_commit();
         }
+        };
+        if (__any_sync(__activemask(), !sl.first_in_frame)) run(std::true_type{}); else run(std::false_type{});
         cp_async_wait<0>();
         // rem only ever decreases: one look tells whether it went negative on the way (:281-283)
-        if (((trouble & FSE_BAD_CODE) | (trouble_of & (32u << 10))) || br.rem() < 0) return CZS_NOT_DECODED;  // placeholder: the exact form decides
+        if (br.rem() < 0) return CZS_NOT_DECODED;  // placeholder: the exact form decides
         return br.rem() > 0 ? CZS_SEQ_EXTRA_BITS : CZS_OK;  // :292-296
     };
 #endif
