@@ -673,7 +673,11 @@ __global__ void __launch_bounds__(FSE_WARPS * 32, 3) k_fse(const czb_frame_desc*
         asm volatile("" : "+r"(llc), "+r"(mlc));  // opaque, as above: one shift and one scaled add per code lookup
         const uint32_t kLL = logLL - 9u, kOF = logOF - 9u, kML = logML - 9u;
         auto prep = [&]() {  // what the next step needs from the entries just looked up
-            lle = lds32(llc + (fse_entry_sym(eLL) << 2)); mle = lds32(mlc + (fse_entry_sym(eML) << 2));
+            // address = table + 4 * symbol as ONE multiply-add (the other pipe); ptxas otherwise makes (entry >> 8) & 0xfc and an add of it
+            uint32_t al, am;
+            asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(al) : "r"(fse_entry_sym(eLL)), "r"(llc));
+            asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(am) : "r"(fse_entry_sym(eML)), "r"(mlc));
+            lle = lds32(al); mle = lds32(am);
             // num_bits = log - floor(log2(next_state)), next_state in the entry's low 10 bits (the shift can go to the other pipe)
             nbLL = kLL + (uint32_t)__clz(eLL << 22); nbML = kML + (uint32_t)__clz(eML << 22); nbOF = kOF + (uint32_t)__clz(eOF << 22);
         };
