@@ -321,3 +321,24 @@ def test_greedy_sequence_frames_are_valid_zstd_and_pin_the_oracle():
         st, out, res = O.decode_frame(frame, dst_cap=len(want))
         assert st == 0 and out == want and res.content_size == len(want), (n_seq, st)
         assert W.libzstd_decompress(frame, len(want)) == want
+
+
+@pytest.mark.parametrize("level", [1, 2, 5, 9, 13, 19])
+def test_oracle_against_libzstd_across_compression_levels(level):
+    """The encoder's choices change with the level (table modes: predefined / RLE / repeat, treeless literals, longer matches, lazy and
+    optimal parsing): whatever libzstd emits at levels 1..19 on text, skewed bytes and a two-symbol alphabet, the oracle decodes it to
+    the original bytes with the frame's checksum, and sees every sequence-table mode at least once over the set."""
+    rng = np.random.default_rng(1000 + level)
+    comp = W.Compressor(level=level)
+    frames, origs = [], []
+    for k in range(6):
+        n = int(rng.integers(300, 300000))
+        kind = k % 3
+        if kind == 0:
+            data = W.synth_text(n, seed=level * 100 + k)
+        elif kind == 1:
+            data = W.skewed_bytes(n, seed=level * 100 + k).tobytes()
+        else:
+            data = bytes(rng.choice(np.array([65, 66], dtype=np.uint8), size=n, p=[0.9, 0.1]).tolist())
+        frames.append(comp.compress(data)); origs.append(bytes(data))
+    _check(frames, origs)
