@@ -308,7 +308,7 @@ def run_b200(args, rank, world, local_rank):
             if tk:
                 roofline["traffic"] = tk["bytes_per_frame"] * frames_per_launch
                 roofline["traffic_source"] = ("profiles/r02_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per frame from this round's "
-                                              "ncu --set full capture of the same kernels (scripts/r02_ncu.sh), x frames per launch")
+                                              "ncu --set full capture of the same kernels (scripts/r02b_final.sh, scripts/ncu_traffic.py), x frames per launch")
                 roofline["algorithmic_bytes_per_launch"] = alg_bytes_per_launch
                 # issue-slot fraction next to the HBM fraction: warp instructions the kernel executes (same capture) against what
                 # the SMs can issue in the kernel's live average launch time (4 schedulers per SM, one warp instruction per cycle)
